@@ -1,0 +1,465 @@
+// Surrogate update kernels (the collector's refit), FP64, sm_100a.
+//   sdb_poly_basis / sdb_poly_fit   replace surrogate_poly.py:68-97  (PHI, normal equations, pinv solve)
+//   sdb_rbf_thin                    replaces surrogate_rbf.py:97-120 (greedy thinning to no_keep)
+//   sdb_rbf_system / sdb_rbf_fit    replace surrogate_rbf.py:91-96,121-130 (distance + kernel matrix,
+//                                   saddle-point system, direct solve through sdb_lu_solve)
+#include <float.h>
+
+#include "sdb_gemm.cuh"
+#include "sdb_models.cuh"
+
+// ===================================================================================================
+// polynomial surrogate
+// ===================================================================================================
+template <int D>
+__global__ void __launch_bounds__(128) poly_basis_kernel(const double *__restrict__ pts, int64_t N, int d, const sdb_model mo,
+                                                         double *__restrict__ PHI) {
+    constexpr int DD = D ? D : SDB_MAX_D;
+    constexpr int UD = D ? D : 1;
+    constexpr int HS = SDB_MAX_DEGREE + 1;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bar = (uint64_t *)smem;
+    unsigned char *p = smem + 16;
+    if (threadIdx.x == 0) {
+        sdb_mbar_init(bar, 1);
+        sdb_mbar_fence_init();
+    }
+    __syncthreads();
+    // only alpha and herm are needed; stage them like the evaluation kernels do (coefs may be NULL)
+    const size_t hb = (size_t)(mo.degree + 1) * (mo.degree + 1) * 8, ab = (size_t)mo.n_terms * d * 4;
+    const double *herm = (const double *)p; sdb_stage_table(p, mo.herm, hb, bar); p += sdb_align16(hb);
+    const int *alpha = (const int *)p;      sdb_stage_table(p, mo.alpha, ab, bar); p += sdb_align16(ab);
+    if (threadIdx.x == 0) sdb_mbar_arrive(bar);
+    sdb_mbar_wait(bar, 0);
+    __syncthreads();
+    const int deg = mo.degree, nh = deg + 1, P = mo.n_terms;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        double h[DD * HS];
+#pragma unroll UD
+        for (int j = 0; j < DD; ++j)
+            if (j < d) {
+                const double x = pts[i * d + j];
+                double pw[HS];
+                pw[0] = 1.0;
+                for (int q = 1; q <= deg; ++q) pw[q] = __dmul_rn(pw[q - 1], x);
+                for (int k = 0; k <= deg; ++k) {
+                    double v = herm[k * nh];
+                    for (int q = 1; q <= k; ++q) v = __dadd_rn(v, __dmul_rn(herm[k * nh + q], pw[q]));
+                    h[j * HS + k] = v;
+                }
+            }
+        for (int t = 0; t < P; ++t) {
+            const int *a = alpha + t * d;
+            double phi = h[a[0]];
+#pragma unroll UD
+            for (int j = 1; j < DD; ++j)
+                if (j < d) phi = __dmul_rn(phi, h[j * HS + a[j]]);
+            PHI[i * P + t] = phi;
+        }
+    }
+}
+
+extern "C" int sdb_poly_basis(const double *d_points, int64_t N, int32_t d, const sdb_model *model, double *d_PHI,
+                              void *stream) {
+    SDB_CHECK_ARG(model && d_points && d_PHI && model->alpha && model->herm, "sdb_poly_basis: NULL pointer");
+    SDB_CHECK_LIMIT(d >= 1 && d <= SDB_MAX_D, "sdb_poly_basis: d=%d outside limits", d);
+    SDB_CHECK_LIMIT(model->degree >= 0 && model->degree <= SDB_MAX_DEGREE, "sdb_poly_basis: degree %d outside [0,%d]",
+                    model->degree, SDB_MAX_DEGREE);
+    if (N <= 0) return SDB_OK;
+    sdb_device_props dp;
+    int rc = sdb_get_device_props(&dp);
+    if (rc) return rc;
+    const size_t smem = 16 + sdb_align16((size_t)(model->degree + 1) * (model->degree + 1) * 8) +
+                        sdb_align16((size_t)model->n_terms * d * 4);
+    SDB_CHECK_LIMIT(smem <= (size_t)dp.smem_optin, "sdb_poly_basis: tables need %zu B of shared memory", smem);
+    int64_t blocks = (N + 127) / 128;
+    if (blocks > (int64_t)dp.sm_count * 16) blocks = (int64_t)dp.sm_count * 16;
+    auto launch = [&](auto kern) -> int {
+        SDB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(d_points, N, d, *model, d_PHI);
+        SDB_CUDA(cudaGetLastError());
+        return SDB_OK;
+    };
+    if (d == 2) return launch(poly_basis_kernel<2>);
+    if (d == 4) return launch(poly_basis_kernel<4>);
+    return launch(poly_basis_kernel<0>);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MAT = pinv(A) RHS for the symmetric P x P matrix A (PHI^T PHI) by one-sided Jacobi (Hestenes):
+// columns of G = A are rotated pairwise until mutually orthogonal; then G = U Sigma, and for a
+// symmetric A the right singular vectors are v_j = sign(u_j^T A u_j) u_j, so
+//   pinv(A) RHS = sum_{sigma_j > cutoff} sign_j / sigma_j * u_j (u_j^T RHS),  cutoff = 1e-15 sigma_max
+// (numpy.linalg.pinv's default rcond).  One CTA; G lives in shared memory when it fits, else in
+// global memory.  Round-robin ordering: P-1 (P even) rounds of P/2 disjoint pairs, one warp per pair.
+// info[0] = number of directions kept, info[1] = sweeps, info[2] = 1 if converged.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) poly_pinv_solve_kernel(const double *__restrict__ A, const double *__restrict__ RHS,
+                                                                  int P, int m, double *__restrict__ MAT,
+                                                                  double *__restrict__ Gglob, int use_smem, int *info) {
+    extern __shared__ __align__(16) double sm[];
+    double *G = use_smem ? sm : Gglob;         // column-major P x P, column j at G + j*P
+    double *sig = use_smem ? sm + (size_t)P * P : Gglob + (size_t)P * P;  // [P] singular values, then signs
+    __shared__ int rotated;
+    __shared__ double s_max;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    for (int e = tid; e < P * P; e += blockDim.x) G[e] = A[e];
+    __syncthreads();
+    const int Pe = (P + 1) & ~1;  // players (one dummy when P is odd)
+    const double tol = 1e-15;
+    int sweeps = 0, converged = 0;
+    for (; sweeps < 60 && !converged; ++sweeps) {
+        if (tid == 0) rotated = 0;
+        __syncthreads();
+        for (int round = 0; round < Pe - 1; ++round) {
+            for (int pair = warp; pair < Pe / 2; pair += nwarp) {
+                // circle method: player Pe-1 fixed, the others rotate
+                int a = (pair == 0) ? Pe - 1 : (round + pair) % (Pe - 1);
+                int b = (round + Pe - 1 - pair) % (Pe - 1);
+                if (a >= P || b >= P) continue;
+                if (a > b) { const int t = a; a = b; b = t; }
+                double *ga = G + (size_t)a * P, *gb = G + (size_t)b * P;
+                double aa = 0.0, bb = 0.0, ab = 0.0;
+                for (int i = lane; i < P; i += 32) {
+                    const double x = ga[i], y = gb[i];
+                    aa = fma(x, x, aa); bb = fma(y, y, bb); ab = fma(x, y, ab);
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    aa += __shfl_xor_sync(0xffffffffu, aa, off);
+                    bb += __shfl_xor_sync(0xffffffffu, bb, off);
+                    ab += __shfl_xor_sync(0xffffffffu, ab, off);
+                }
+                if (fabs(ab) > tol * sqrt(aa * bb) && ab != 0.0) {
+                    const double zeta = (bb - aa) / (2.0 * ab);
+                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                    for (int i = lane; i < P; i += 32) {
+                        const double x = ga[i], y = gb[i];
+                        ga[i] = c * x - s * y;
+                        gb[i] = s * x + c * y;
+                    }
+                    if (lane == 0) rotated = 1;
+                }
+            }
+            __syncthreads();
+        }
+        converged = !rotated;
+        __syncthreads();
+    }
+    // singular values and sign of the eigenvalue
+    if (tid == 0) s_max = 0.0;
+    __syncthreads();
+    for (int j = warp; j < P; j += nwarp) {
+        const double *g = G + (size_t)j * P;
+        double nn = 0.0;
+        for (int i = lane; i < P; i += 32) nn = fma(g[i], g[i], nn);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, off);
+        // u^T A u has the sign of g^T A g
+        double q = 0.0;
+        for (int i = lane; i < P; i += 32) {
+            double r = 0.0;
+            for (int k = 0; k < P; ++k) r = fma(A[(size_t)k * P + i], g[k], r);
+            q = fma(g[i], r, q);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
+        if (lane == 0) sig[j] = copysign(sqrt(nn), q);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double mx = 0.0;
+        for (int j = 0; j < P; ++j) mx = fmax(mx, fabs(sig[j]));
+        s_max = mx;
+        int kept = 0;
+        for (int j = 0; j < P; ++j) kept += fabs(sig[j]) > 1e-15 * mx;
+        info[0] = kept; info[1] = sweeps; info[2] = converged;
+    }
+    __syncthreads();
+    const double cutoff = 1e-15 * s_max;
+    // MAT[:, k] = sum_j sign_j / sigma_j^3 * g_j (g_j^T RHS[:, k])   (u_j = g_j / sigma_j)
+    for (int e = tid; e < P * m; e += blockDim.x) MAT[e] = 0.0;
+    __syncthreads();
+    // one warp per observation column; directions summed in index order (deterministic)
+    for (int k = warp; k < m; k += nwarp) {
+        for (int j = 0; j < P; ++j) {
+            const double sj = fabs(sig[j]);
+            if (!(sj > cutoff)) continue;
+            const double *g = G + (size_t)j * P;
+            double dot = 0.0;
+            for (int i = lane; i < P; i += 32) dot = fma(g[i], RHS[(size_t)i * m + k], dot);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+            const double w = copysign(1.0, sig[j]) * ((dot / sj) / sj) / sj;
+            for (int i = lane; i < P; i += 32) MAT[(size_t)i * m + k] = fma(w, g[i], MAT[(size_t)i * m + k]);
+        }
+    }
+}
+
+static int poly_gram_slabs(int64_t n, int P) {
+    // enough K-slabs to fill the GPU for small P; bounded workspace
+    const int tiles = ((P + GM_BM - 1) / GM_BM) * ((P + GM_BN - 1) / GM_BN);
+    int64_t s = (148 * 4 + tiles - 1) / tiles;
+    const int64_t by_k = (n + 255) / 256;
+    if (s > by_k) s = by_k;
+    if (s < 1) s = 1;
+    if (s > 1024) s = 1024;
+    return (int)s;
+}
+
+extern "C" int64_t sdb_poly_fit_work(int64_t n, int32_t P, int32_t m) {
+    const int64_t slabs = poly_gram_slabs(n, P);
+    // PHI [n x P] | A [P x P] | RHS [P x m] | G + sigma (P*P + P) | slab workspace for the larger of the two products
+    const int64_t cmax = (int64_t)P * (P > m ? P : m);
+    return n * P + (int64_t)P * P + (int64_t)P * m + (int64_t)P * P + P + slabs * cmax + 64;
+}
+
+extern "C" int sdb_poly_fit(const double *d_X, const double *d_Y, int64_t n, int32_t d, int32_t m, const sdb_model *model,
+                            double *d_MAT, double *d_work, int32_t *d_info, void *stream) {
+    SDB_CHECK_ARG(d_X && d_Y && model && d_MAT && d_work && d_info, "sdb_poly_fit: NULL pointer");
+    SDB_CHECK_ARG(n >= 1 && n < ((int64_t)1 << 31), "sdb_poly_fit: n = %lld out of range", (long long)n);
+    SDB_CHECK_LIMIT(m >= 1 && m <= SDB_MAX_M, "sdb_poly_fit: m=%d outside limits", m);
+    const int P = model->n_terms;
+    SDB_CHECK_ARG(P >= 1, "sdb_poly_fit: n_terms must be >= 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    sdb_device_props dp;
+    int rc = sdb_get_device_props(&dp);
+    if (rc) return rc;
+    double *PHI = d_work;
+    double *A = PHI + n * P;
+    double *RHS = A + (int64_t)P * P;
+    double *Gg = RHS + (int64_t)P * m;
+    double *slab = Gg + (int64_t)P * P + P;
+    rc = sdb_poly_basis(d_X, n, d, model, PHI, stream);
+    if (rc) return rc;
+    const int slabs = poly_gram_slabs(n, P);
+    // A = PHI^T PHI  (column-major P x P; symmetric).  PHI is row-major n x P: PHI^T(i,k) = PHI[k*P+i].
+    rc = sdb_gemm(st, P, P, (int)n, 1.0, PHI, 1, P, PHI, P, 1, 0.0, A, P, slabs, slab);
+    if (rc) return rc;
+    // RHS = PHI^T Y, stored row-major [P x m] == column-major m x P: compute its transpose Y^T PHI
+    // (M = m, N = P): A-operand Y^T(i,k) = Y[k*m+i], B-operand PHI(k,j) = PHI[k*P+j].
+    rc = sdb_gemm(st, m, P, (int)n, 1.0, d_Y, 1, m, PHI, P, 1, 0.0, RHS, m, slabs, slab);
+    if (rc) return rc;
+    const size_t need = ((size_t)P * P + P) * 8;
+    const int use_smem = need + 1024 <= (size_t)dp.smem_optin;
+    const size_t smem = use_smem ? need : 0;
+    SDB_CUDA(cudaFuncSetAttribute((const void *)poly_pinv_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(use_smem ? need : 0)));
+    poly_pinv_solve_kernel<<<1, 1024, smem, st>>>(A, RHS, P, m, d_MAT, Gg, use_smem, d_info);
+    SDB_CUDA(cudaGetLastError());
+    return SDB_OK;
+}
+
+// ===================================================================================================
+// RBF surrogate
+// ===================================================================================================
+// distance exactly as the reference forms it: sum_k (x_jk - x_ik)^2 with separately rounded
+// square and add (np.power(Q-T, 2) accumulated k = 0..d-1), then an IEEE square root.
+__device__ __forceinline__ double ref_distance(const double *__restrict__ xi, const double *__restrict__ xj, int d) {
+    double s = 0.0;
+    for (int k = 0; k < d; ++k) {
+        const double df = __dadd_rn(xj[k], -xi[k]);
+        s = __dadd_rn(s, __dmul_rn(df, df));
+    }
+    return __dsqrt_rn(s);
+}
+
+__device__ __forceinline__ double ref_phi(double r, int kt) {
+    switch (kt) {
+        case 1: return r * r * r;
+        case 2: { const double r2 = r * r; return r2 * r2 * r; }
+        case 3: { const double r2 = r * r; return r2 * r2 * r2 * r; }
+        case 7: { const double r2 = r * r, r4 = r2 * r2; return r4 * r4 * r; }
+        case 4: return exp(-(r * r));
+        case 5: return 1.0 / sqrt(r * r + 1.0);
+        default: return r;  // 0, and 6 (a no-op in the reference)
+    }
+}
+
+// S [(n+d+1)^2] (symmetric, so row- and column-major coincide) and RHS as m contiguous columns [m][n+d+1].
+__global__ void __launch_bounds__(256) rbf_system_kernel(const double *__restrict__ X, const double *__restrict__ Y, int n, int d,
+                                                         int m, int kt, double *__restrict__ S, double *__restrict__ RHS) {
+    const int N = n + d + 1;
+    const int i = blockIdx.x * 16 + (threadIdx.x & 15);  // fast index: contiguous in memory
+    const int j = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (i < N && j < N) {
+        double v;
+        if (i < n && j < n) v = ref_phi(ref_distance(X + (size_t)i * d, X + (size_t)j * d, d), kt);
+        else if (i < n) v = (j - n < d) ? X[(size_t)i * d + (j - n)] : 1.0;
+        else if (j < n) v = (i - n < d) ? X[(size_t)j * d + (i - n)] : 1.0;
+        else v = 0.0;
+        S[(size_t)j * N + i] = v;
+    }
+    if (RHS && blockIdx.y == 0 && (threadIdx.x >> 4) == 0 && i < N)
+        for (int k = 0; k < m; ++k) RHS[(size_t)k * N + i] = i < n ? Y[(size_t)i * m + k] : 0.0;
+}
+
+extern "C" int sdb_rbf_system(const double *d_X, const double *d_Y, int64_t n, int32_t d, int32_t m, int32_t kernel_type,
+                              double *d_S, double *d_RHS, void *stream) {
+    SDB_CHECK_ARG(d_X && d_S && (d_Y || !d_RHS), "sdb_rbf_system: NULL pointer");
+    SDB_CHECK_ARG(n >= 1 && n < (1 << 30), "sdb_rbf_system: n out of range");
+    SDB_CHECK_LIMIT(d >= 1 && d <= SDB_MAX_D && m >= 1 && m <= SDB_MAX_M, "sdb_rbf_system: d=%d m=%d outside limits", d, m);
+    SDB_CHECK_ARG(kernel_type >= 0 && kernel_type <= 7, "sdb_rbf_system: kernel_type %d outside [0,7]", kernel_type);
+    const int N = (int)n + d + 1;
+    dim3 grid((N + 15) / 16, (N + 15) / 16);
+    rbf_system_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_X, d_Y, (int)n, d, m, kernel_type, d_S, d_RHS);
+    SDB_CUDA(cudaGetLastError());
+    return SDB_OK;
+}
+
+__global__ void __launch_bounds__(256) transpose_out_kernel(const double *__restrict__ Xc, int N, int m, double *__restrict__ out) {
+    // Xc: m columns of length N  ->  out [N x m] row-major
+    const int64_t total = (int64_t)N * m;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / m), k = (int)(e % m);
+        out[e] = Xc[(size_t)k * N + i];
+    }
+}
+
+extern "C" int64_t sdb_rbf_fit_work(int64_t n, int32_t d, int32_t m) {
+    const int64_t N = n + d + 1;
+    return N * N + N * m + N / 2 + 64;  // system | right-hand sides | pivots (int32)
+}
+
+extern "C" int sdb_rbf_fit(const double *d_X, const double *d_Y, int64_t n, int32_t d, int32_t m, int32_t kernel_type,
+                           double *d_COEFS, double *d_work, int32_t *d_info, void *stream) {
+    SDB_CHECK_ARG(d_X && d_Y && d_COEFS && d_work && d_info, "sdb_rbf_fit: NULL pointer");
+    const int64_t N = n + d + 1;
+    double *S = d_work;
+    double *RHS = S + N * N;
+    int32_t *piv = (int32_t *)(RHS + N * m);
+    int rc = sdb_rbf_system(d_X, d_Y, n, d, m, kernel_type, S, RHS, stream);
+    if (rc) return rc;
+    rc = sdb_lu_solve(S, N, RHS, m, piv, d_info, stream);
+    if (rc) return rc;
+    int64_t blocks = (N * m + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    transpose_out_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(RHS, (int)N, m, d_COEFS);
+    SDB_CUDA(cudaGetLastError());
+    return SDB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Greedy thinning (surrogate_rbf.py:97-120): repeatedly find the globally closest pair -- the first
+// flat arg-min of the symmetric distance matrix, i.e. the smallest row index among the minima, then the
+// smallest column index -- and drop the point owning that ROW, until no_keep points remain.
+// The n x n matrix is never stored: each point keeps (distance, index) of its nearest alive neighbour
+// (ties -> smallest index); removing a point only invalidates the rows that pointed at it.
+//   kernel 1 (grid): nearest neighbour of every point.   kernel 2 (one CTA): the removal loop.
+// work: nn_dist [n] doubles | nn_idx [n] int32
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) thin_nearest_kernel(const double *__restrict__ X, int n, int d, double *__restrict__ nn_dist,
+                                                           int *__restrict__ nn_idx) {
+    // one warp per row
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double best = DBL_MAX;
+    int bj = INT_MAX;
+    for (int j = lane; j < n; j += 32) {
+        if (j == row) continue;
+        const double r = ref_distance(X + (size_t)row * d, X + (size_t)j * d, d);
+        if (r < best) { best = r; bj = j; }   // j ascending per lane: first minimum kept
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+        if (ov < best || (ov == best && oj < bj)) { best = ov; bj = oj; }
+    }
+    if (lane == 0) { nn_dist[row] = best; nn_idx[row] = bj; }
+}
+
+__global__ void __launch_bounds__(1024, 1) thin_remove_kernel(const double *__restrict__ X, int n, int d, int no_keep,
+                                                              double *__restrict__ nn_dist, int *__restrict__ nn_idx,
+                                                              uint8_t *__restrict__ keep) {
+    __shared__ double rv[32];
+    __shared__ int rr[32];
+    __shared__ int victim;
+    __shared__ int todo[1024];
+    __shared__ int ntodo;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < n; i += blockDim.x) keep[i] = 1;
+    __syncthreads();
+    for (int it = 0; it < n - no_keep; ++it) {
+        // global minimum over alive rows; ties -> smallest row
+        double best = DBL_MAX;
+        int brow = INT_MAX;
+        for (int i = tid; i < n; i += blockDim.x)
+            if (keep[i] && nn_idx[i] != INT_MAX && nn_dist[i] < best) { best = nn_dist[i]; brow = i; }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, off);
+            const int orow = __shfl_xor_sync(0xffffffffu, brow, off);
+            if (ov < best || (ov == best && orow < brow)) { best = ov; brow = orow; }
+        }
+        if (lane == 0) { rv[warp] = best; rr[warp] = brow; }
+        __syncthreads();
+        if (warp == 0) {
+            best = rv[lane]; brow = rr[lane];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, off);
+                const int orow = __shfl_xor_sync(0xffffffffu, brow, off);
+                if (ov < best || (ov == best && orow < brow)) { best = ov; brow = orow; }
+            }
+            if (lane == 0) { victim = brow; ntodo = 0; }
+        }
+        __syncthreads();
+        const int v = victim;
+        if (v == INT_MAX) break;  // fewer than two alive points
+        if (tid == 0) keep[v] = 0;
+        __syncthreads();
+        // rows whose nearest neighbour was the victim must be rescanned
+        for (int base = 0; base < n; base += 1024) {
+            const int i = base + tid;
+            if (i < n && keep[i] && nn_idx[i] == v) {
+                const int slot = atomicAdd(&ntodo, 1);
+                todo[slot] = i;   // at most 1024 per chunk
+            }
+            __syncthreads();
+            const int cnt = ntodo;
+            for (int t = warp; t < cnt; t += 32) {
+                const int row = todo[t];
+                double b = DBL_MAX;
+                int bj = INT_MAX;
+                for (int j = lane; j < n; j += 32) {
+                    if (j == row || !keep[j]) continue;
+                    const double r = ref_distance(X + (size_t)row * d, X + (size_t)j * d, d);
+                    if (r < b) { b = r; bj = j; }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, b, off);
+                    const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+                    if (ov < b || (ov == b && oj < bj)) { b = ov; bj = oj; }
+                }
+                if (lane == 0) { nn_dist[row] = b; nn_idx[row] = bj; }
+            }
+            __syncthreads();
+            if (tid == 0) ntodo = 0;
+            __syncthreads();
+        }
+    }
+}
+
+extern "C" int64_t sdb_rbf_thin_work(int64_t n) { return n + n / 2 + 64; }
+
+extern "C" int sdb_rbf_thin(const double *d_X, int64_t n, int32_t d, int64_t no_keep, uint8_t *d_keep, double *d_work,
+                            void *stream) {
+    SDB_CHECK_ARG(d_X && d_keep && d_work, "sdb_rbf_thin: NULL pointer");
+    SDB_CHECK_ARG(n >= 1 && n < (1 << 30) && no_keep >= 0, "sdb_rbf_thin: bad sizes");
+    SDB_CHECK_LIMIT(d >= 1 && d <= SDB_MAX_D, "sdb_rbf_thin: d=%d outside limits", d);
+    cudaStream_t st = (cudaStream_t)stream;
+    double *nn_dist = d_work;
+    int *nn_idx = (int *)(d_work + n);
+    if (no_keep >= n) {
+        SDB_CUDA(cudaMemsetAsync(d_keep, 1, (size_t)n, st));
+        return SDB_OK;
+    }
+    thin_nearest_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(d_X, (int)n, d, nn_dist, nn_idx);
+    thin_remove_kernel<<<1, 1024, 0, st>>>(d_X, (int)n, d, (int)no_keep, nn_dist, nn_idx, d_keep);
+    SDB_CUDA(cudaGetLastError());
+    return SDB_OK;
+}

@@ -1,0 +1,174 @@
+// Internal FP64 GEMM on the tensor pipe (mma.sync m8n8k4 f64 -> DMMA), generic strides.
+//
+//   C[M x N] (column-major, ldc)  =  beta * C  +  alpha * A[M x K] * B[K x N]
+//   A(i,k) = A[i*sa_m + k*sa_k],  B(k,j) = B[k*sb_k + j*sb_n]      (any transposition via strides)
+//
+// Split-K: gridDim.z slabs of the K range; slab z writes alpha * (partial product) to
+// C + z*c_slab (beta ignored) and a second kernel (sdb_gemm_reduce) sums the slabs in a fixed order
+// -- deterministic, no atomics.  gridDim.z == 1 writes C directly.
+//
+// Used by: LU trailing updates / triangular solves (sdb_lu.cu), normal equations of the polynomial
+// fit (sdb_fit.cu).  Tile 128 x 64 x 8, 256 threads = 8 warps (4 x 2), warp tile 32 x 32,
+// two-stage shared-memory pipeline, register prefetch of the next k-slab.
+#pragma once
+#include "sdb_common.cuh"
+
+#define GM_BM 128
+#define GM_BN 64
+#define GM_BK 8
+#define GM_PAD 8  // row stride == 8 (mod 16) doubles: the 4 k-rows of a fragment load hit disjoint bank halves
+
+__device__ __forceinline__ void sdb_dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+struct sdb_gemm_args {
+    const double *A, *B;
+    double *C;
+    int64_t sa_m, sa_k, sb_k, sb_n, ldc, c_slab;
+    int M, N, K;
+    int k_per_slab;  // multiple of GM_BK
+    double alpha, beta;
+};
+
+static __global__ void __launch_bounds__(256) sdb_gemm_kernel(const sdb_gemm_args g) {
+    __shared__ double As[2][GM_BK][GM_BM + GM_PAD];
+    __shared__ double Bs[2][GM_BK][GM_BN + GM_PAD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+    const int m0 = blockIdx.x * GM_BM, n0 = blockIdx.y * GM_BN;
+    const int kbeg = blockIdx.z * g.k_per_slab;
+    const int kend = min(g.K, kbeg + g.k_per_slab);
+    const int gid = lane >> 2, tig = lane & 3;
+
+    // global -> register staging: A tile 128 x 8 = 1024 elements = 4 per thread, B tile 64 x 8 = 2 per thread
+    const bool a_m_fast = g.sa_m <= g.sa_k;  // which index runs fastest over consecutive threads
+    const bool b_n_fast = g.sb_n <= g.sb_k;
+    double ra[4], rb[2];
+    auto load_tiles = [&](int k0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int idx = tid + e * 256;
+            const int mm = a_m_fast ? (idx % GM_BM) : (idx / GM_BK);
+            const int kk = a_m_fast ? (idx / GM_BM) : (idx % GM_BK);
+            const int gm = m0 + mm, gk = k0 + kk;
+            ra[e] = (gm < g.M && gk < kend) ? g.A[(int64_t)gm * g.sa_m + (int64_t)gk * g.sa_k] : 0.0;
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int idx = tid + e * 256;
+            const int nn = b_n_fast ? (idx % GM_BN) : (idx / GM_BK);
+            const int kk = b_n_fast ? (idx / GM_BN) : (idx % GM_BK);
+            const int gn = n0 + nn, gk = k0 + kk;
+            rb[e] = (gn < g.N && gk < kend) ? g.B[(int64_t)gk * g.sb_k + (int64_t)gn * g.sb_n] : 0.0;
+        }
+    };
+    auto store_tiles = [&](int st) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int idx = tid + e * 256;
+            const int mm = a_m_fast ? (idx % GM_BM) : (idx / GM_BK);
+            const int kk = a_m_fast ? (idx / GM_BM) : (idx % GM_BK);
+            As[st][kk][mm] = ra[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int idx = tid + e * 256;
+            const int nn = b_n_fast ? (idx % GM_BN) : (idx / GM_BK);
+            const int kk = b_n_fast ? (idx / GM_BN) : (idx % GM_BK);
+            Bs[st][kk][nn] = rb[e];
+        }
+    };
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    int st = 0;
+    if (kbeg < kend) {
+        load_tiles(kbeg);
+        store_tiles(0);
+    }
+    __syncthreads();
+    for (int k0 = kbeg; k0 < kend; k0 += GM_BK) {
+        const bool more = k0 + GM_BK < kend;
+        if (more) load_tiles(k0 + GM_BK);
+#pragma unroll
+        for (int ks = 0; ks < GM_BK; ks += 4) {
+            double fa[4], fb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) fa[i] = As[st][ks + tig][wm + i * 8 + gid];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) fb[j] = Bs[st][ks + tig][wn + j * 8 + gid];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sdb_dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+        }
+        if (more) store_tiles(st ^ 1);
+        __syncthreads();
+        st ^= 1;
+    }
+    // epilogue: accumulator (row gid, cols 2*tig, 2*tig+1) of each 8x8 tile
+    double *Cz = g.C + (int64_t)blockIdx.z * g.c_slab;
+    const bool direct = gridDim.z == 1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gm = m0 + wm + i * 8 + gid, gn = n0 + wn + j * 8 + tig * 2 + e;
+                if (gm < g.M && gn < g.N) {
+                    double *p = Cz + (int64_t)gn * g.ldc + gm;
+                    const double v = g.alpha * acc[i][j][e];
+                    *p = (direct && g.beta != 0.0) ? fma(g.beta, *p, v) : v;
+                }
+            }
+}
+
+// C = beta*C + sum_z slab_z   (fixed order z = 0, 1, ...)
+static __global__ void __launch_bounds__(256) sdb_gemm_reduce(double *C, int64_t ldc, const double *slabs, int64_t c_slab,
+                                                       int64_t ld_slab, int M, int N, int nslab, double beta) {
+    const int64_t total = (int64_t)M * N;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e % M), j = (int)(e / M);
+        double s = 0.0;
+        for (int z = 0; z < nslab; ++z) s += slabs[(int64_t)z * c_slab + (int64_t)j * ld_slab + i];
+        double *p = C + (int64_t)j * ldc + i;
+        *p = (beta != 0.0) ? fma(beta, *p, s) : s;
+    }
+}
+
+// Host launcher.  `slab_ws` (doubles, >= nslab * M * N) is needed only when nslab > 1.
+static inline int sdb_gemm(cudaStream_t st, int M, int N, int K, double alpha, const double *A, int64_t sa_m, int64_t sa_k,
+                           const double *B, int64_t sb_k, int64_t sb_n, double beta, double *C, int64_t ldc, int nslab = 1,
+                           double *slab_ws = nullptr) {
+    if (M <= 0 || N <= 0) return SDB_OK;
+    sdb_gemm_args g;
+    g.A = A; g.B = B; g.sa_m = sa_m; g.sa_k = sa_k; g.sb_k = sb_k; g.sb_n = sb_n;
+    g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta;
+    if (nslab < 1) nslab = 1;
+    int kps = ((K + nslab - 1) / nslab + GM_BK - 1) / GM_BK * GM_BK;
+    if (kps < GM_BK) kps = GM_BK;
+    nslab = (K + kps - 1) / kps;
+    if (nslab < 1) nslab = 1;
+    g.k_per_slab = kps;
+    dim3 grid((M + GM_BM - 1) / GM_BM, (N + GM_BN - 1) / GM_BN, nslab);
+    if (nslab == 1) {
+        g.C = C; g.ldc = ldc; g.c_slab = 0;
+        sdb_gemm_kernel<<<grid, 256, 0, st>>>(g);
+    } else {
+        g.C = slab_ws; g.ldc = M; g.c_slab = (int64_t)M * N;
+        sdb_gemm_kernel<<<grid, 256, 0, st>>>(g);
+        int64_t blocks = ((int64_t)M * N + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        sdb_gemm_reduce<<<(unsigned)blocks, 256, 0, st>>>(C, ldc, slab_ws, (int64_t)M * N, M, M, N, nslab, beta);
+    }
+    SDB_CUDA(cudaGetLastError());
+    return SDB_OK;
+}

@@ -1,0 +1,337 @@
+// Device functions: forward models (poly / RBF / toy), Gaussian log-posterior.
+// Everything here works on models whose tables already sit in shared memory.
+#pragma once
+#include "sdb_common.cuh"
+
+// A model whose tables have been staged into shared memory.
+struct sdb_smodel {
+    int kind, kernel_type, degree, n_terms;
+    int n_centers;
+    const double *coefs;    // smem
+    const double *centers;  // smem
+    const int *alpha;       // smem
+    const double *herm;     // smem
+    double toy_f, toy_L, toy_M;
+};
+
+// bytes of shared memory a model needs (each table rounded up to 16 B)
+__host__ __device__ inline size_t sdb_align16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+__host__ __device__ inline size_t sdb_model_smem_bytes(const sdb_model &mo, int d, int m) {
+    if (mo.kind == SDB_MODEL_RBF)
+        return sdb_align16((size_t)mo.n_centers * d * 8) + sdb_align16((size_t)(mo.n_centers + d + 1) * m * 8);
+    if (mo.kind == SDB_MODEL_POLY)
+        return sdb_align16((size_t)mo.n_terms * m * 8) + sdb_align16((size_t)(mo.degree + 1) * (mo.degree + 1) * 8) +
+               sdb_align16((size_t)mo.n_terms * d * 4);
+    return 0;
+}
+
+// Stage one table: thread 0 issues the 16-byte-granular part as TMA bulk copies on `bar`,
+// the (<16 B) tail goes through ordinary 4-byte loads.  Call from all threads of the CTA.
+__device__ __forceinline__ void sdb_stage_table(void *dst, const void *src, size_t bytes, uint64_t *bar) {
+    const size_t bulk = bytes & ~(size_t)15;
+    if (threadIdx.x == 0 && bulk) sdb_bulk_stage(dst, src, bulk, bar);
+    const size_t tail_words = (bytes - bulk) >> 2;
+    if (threadIdx.x < tail_words)
+        ((uint32_t *)((char *)dst + bulk))[threadIdx.x] = ((const uint32_t *)((const char *)src + bulk))[threadIdx.x];
+}
+
+// Carve `base` for model `mo`, start the copies, return the smem view.  All threads call it.
+__device__ inline sdb_smodel sdb_stage_model(const sdb_model &mo, int d, int m, unsigned char *&base, uint64_t *bar) {
+    sdb_smodel s;
+    s.kind = mo.kind; s.kernel_type = mo.kernel_type; s.degree = mo.degree; s.n_terms = mo.n_terms;
+    s.n_centers = (int)mo.n_centers;
+    s.coefs = nullptr; s.centers = nullptr; s.alpha = nullptr; s.herm = nullptr;
+    s.toy_f = mo.toy_f; s.toy_L = mo.toy_L; s.toy_M = mo.toy_M;
+    if (mo.kind == SDB_MODEL_RBF) {
+        const size_t cb = (size_t)mo.n_centers * d * 8, wb = (size_t)(mo.n_centers + d + 1) * m * 8;
+        s.centers = (const double *)base; sdb_stage_table(base, mo.centers, cb, bar); base += sdb_align16(cb);
+        s.coefs = (const double *)base;   sdb_stage_table(base, mo.coefs, wb, bar);   base += sdb_align16(wb);
+    } else if (mo.kind == SDB_MODEL_POLY) {
+        const size_t mb = (size_t)mo.n_terms * m * 8, hb = (size_t)(mo.degree + 1) * (mo.degree + 1) * 8,
+                     ab = (size_t)mo.n_terms * d * 4;
+        s.coefs = (const double *)base; sdb_stage_table(base, mo.coefs, mb, bar); base += sdb_align16(mb);
+        s.herm = (const double *)base;  sdb_stage_table(base, mo.herm, hb, bar);  base += sdb_align16(hb);
+        s.alpha = (const int *)base;    sdb_stage_table(base, mo.alpha, ab, bar); base += sdb_align16(ab);
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------
+// Polynomial surrogate, one point per thread (surrogate_poly.py:18-30,162-175).
+// Univariate values by monomial accumulation in the reference's order, products left to
+// right, both with separately rounded multiply/add so PHI is bit-identical to numpy's;
+// only the final PHI.MAT contraction uses fma (BLAS order is not reproducible anyway).
+// ---------------------------------------------------------------------------------------
+template <int D, int M>
+__device__ __forceinline__ void sdb_poly_point(const sdb_smodel &s, int d, int m, const double *x, double *out) {
+    constexpr int DD = D ? D : SDB_MAX_D;
+    constexpr int UD = D ? D : 1;  // unroll only the specialised sizes
+    constexpr int HS = SDB_MAX_DEGREE + 1;
+    const int deg = s.degree, nh = deg + 1;
+    double h[DD * HS];
+#pragma unroll UD
+    for (int j = 0; j < DD; ++j) {
+        if (j < d) {
+            double pw[HS];
+            pw[0] = 1.0;
+            for (int i = 1; i <= deg; ++i) pw[i] = __dmul_rn(pw[i - 1], x[j]);
+            for (int k = 0; k <= deg; ++k) {
+                double v = s.herm[k * nh];
+                for (int i = 1; i <= k; ++i) {   // coefficients above the diagonal are zero: adding 0*x^i is exact
+                    v = __dadd_rn(v, __dmul_rn(s.herm[k * nh + i], pw[i]));
+                }
+                h[j * HS + k] = v;
+            }
+        }
+    }
+    constexpr int MM = M ? M : SDB_MAX_M;
+    constexpr int UM = M ? M : 1;
+#pragma unroll UM
+    for (int k = 0; k < MM; ++k)
+        if (k < m) out[k] = 0.0;
+    for (int t = 0; t < s.n_terms; ++t) {
+        const int *a = s.alpha + t * d;
+        double phi = h[a[0]];                     // 1 * h = h exactly
+#pragma unroll UD
+        for (int j = 1; j < DD; ++j)
+            if (j < d) phi = __dmul_rn(phi, h[j * HS + a[j]]);
+#pragma unroll UM
+        for (int k = 0; k < MM; ++k)
+            if (k < m) out[k] = fma(phi, s.coefs[t * m + k], out[k]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// RBF surrogate (surrogate_rbf.py:20-40): partial sums over centers i = first, first+stride, ...
+// ---------------------------------------------------------------------------------------
+template <int D, int M, int KT>
+__device__ __forceinline__ void sdb_rbf_partial_kt(const sdb_smodel &s, int d, int m, const double *x, double *acc,
+                                                   int first, int stride) {
+    constexpr int DD = D ? D : SDB_MAX_D;
+    constexpr int UD = D ? D : 1;  // unroll only the specialised sizes
+    constexpr int MM = M ? M : SDB_MAX_M;
+    constexpr int UM = M ? M : 1;
+    const int n = s.n_centers;
+#pragma unroll 4
+    for (int i = first; i < n; i += stride) {
+        const double *c = s.centers + (size_t)i * d;
+        double r2 = 0.0;
+#pragma unroll UD
+        for (int j = 0; j < DD; ++j)
+            if (j < d) {
+                const double df = c[j] - x[j];
+                r2 = fma(df, df, r2);
+            }
+        const double phi = sdb_rbf_phi(r2, KT);
+        const double *w = s.coefs + (size_t)i * m;
+#pragma unroll UM
+        for (int k = 0; k < MM; ++k)
+            if (k < m) acc[k] = fma(phi, w[k], acc[k]);
+    }
+}
+
+template <int D, int M>
+__device__ __forceinline__ void sdb_rbf_partial(const sdb_smodel &s, int d, int m, const double *x, double *acc,
+                                                int first, int stride) {
+    switch (s.kernel_type) {
+        case 1: sdb_rbf_partial_kt<D, M, 1>(s, d, m, x, acc, first, stride); break;
+        case 2: sdb_rbf_partial_kt<D, M, 2>(s, d, m, x, acc, first, stride); break;
+        case 3: sdb_rbf_partial_kt<D, M, 3>(s, d, m, x, acc, first, stride); break;
+        case 4: sdb_rbf_partial_kt<D, M, 4>(s, d, m, x, acc, first, stride); break;
+        case 5: sdb_rbf_partial_kt<D, M, 5>(s, d, m, x, acc, first, stride); break;
+        case 7: sdb_rbf_partial_kt<D, M, 7>(s, d, m, x, acc, first, stride); break;
+        default: sdb_rbf_partial_kt<D, M, 0>(s, d, m, x, acc, first, stride); break;
+    }
+}
+
+// linear tail: COEFS[n+d] + sum_j x_j * COEFS[n+j]   (surrogate_rbf.py:38)
+template <int D, int M>
+__device__ __forceinline__ void sdb_rbf_add_tail(const sdb_smodel &s, int d, int m, const double *x, double *acc) {
+    constexpr int DD = D ? D : SDB_MAX_D;
+    constexpr int UD = D ? D : 1;  // unroll only the specialised sizes
+    constexpr int MM = M ? M : SDB_MAX_M;
+    constexpr int UM = M ? M : 1;
+    const double *lin = s.coefs + (size_t)s.n_centers * m;
+#pragma unroll UM
+    for (int k = 0; k < MM; ++k)
+        if (k < m) {
+            double t = 0.0;
+#pragma unroll UD
+            for (int j = 0; j < DD; ++j)
+                if (j < d) t = fma(x[j], lin[j * m + k], t);
+            acc[k] += lin[d * m + k] + t;
+        }
+}
+
+// L lanes (a power of two, aligned inside a warp) share one point: lane `sub` takes centers
+// sub, sub+L, ...; an xor butterfly leaves the identical total on all L lanes.
+template <int D, int M>
+__device__ __forceinline__ void sdb_rbf_point_split(const sdb_smodel &s, int d, int m, const double *x, double *out,
+                                                    int sub, int L) {
+    constexpr int MM = M ? M : SDB_MAX_M;
+    constexpr int UM = M ? M : 1;
+#pragma unroll UM
+    for (int k = 0; k < MM; ++k)
+        if (k < m) out[k] = 0.0;
+    sdb_rbf_partial<D, M>(s, d, m, x, out, sub, L);
+    for (int off = L >> 1; off > 0; off >>= 1) {
+#pragma unroll UM
+        for (int k = 0; k < MM; ++k)
+            if (k < m) out[k] += sdb_shfl_xor(out[k], off);
+    }
+    sdb_rbf_add_tail<D, M>(s, d, m, x, out);
+}
+
+// Warp-cooperative evaluation for a data-dependent subset of chains (the "true model" after a
+// stage-1 pass): every lane whose `need` is set and that is the first lane of its L-group gets
+// served in turn; all 32 lanes split the centers of that one point.  Must be called by the full
+// warp, converged.  Lanes with need set receive the result in out[].
+template <int D, int M>
+__device__ __forceinline__ void sdb_rbf_point_warp(const sdb_smodel &s, int d, int m, const double *x, double *out,
+                                                   bool need, int L) {
+    constexpr int DD = D ? D : SDB_MAX_D;
+    constexpr int UD = D ? D : 1;  // unroll only the specialised sizes
+    constexpr int MM = M ? M : SDB_MAX_M;
+    constexpr int UM = M ? M : 1;
+    const int lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(0xffffffffu, need && ((lane & (L - 1)) == 0));
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        double xs[DD], acc[MM];
+#pragma unroll UD
+        for (int j = 0; j < DD; ++j)
+            if (j < d) xs[j] = sdb_shfl(x[j], src);
+#pragma unroll UM
+        for (int k = 0; k < MM; ++k)
+            if (k < m) acc[k] = 0.0;
+        sdb_rbf_partial<D, M>(s, d, m, xs, acc, lane, 32);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll UM
+            for (int k = 0; k < MM; ++k)
+                if (k < m) acc[k] += sdb_shfl_xor(acc[k], off);
+        }
+        sdb_rbf_add_tail<D, M>(s, d, m, xs, acc);
+        if ((lane / L) == (src / L)) {
+#pragma unroll UM
+            for (int k = 0; k < MM; ++k)
+                if (k < m) out[k] = acc[k];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Toy model (examples/solvers/solver_examples.py:20-29), the reference's operation order with
+// separately rounded operations; bit-identical to numpy given the same exp().
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double sdb_toy_G(const sdb_smodel &s, const double *x) {
+    const double f = s.toy_f, L = s.toy_L, Mm = s.toy_M;
+    const double k1 = exp(x[0]), k2 = exp(x[1]);
+    const double D1 = __ddiv_rn(__dmul_rn(f, L), k2);
+    const double C1 = __ddiv_rn(__dmul_rn(D1, k2), k1);
+    const double MM2 = __dmul_rn(Mm, Mm), LL2 = __dmul_rn(L, L);
+    const double a = __dmul_rn(__ddiv_rn(-f, __dmul_rn(2.0, k1)), MM2);
+    const double b = __dmul_rn(C1, Mm);
+    const double c = __dmul_rn(__ddiv_rn(f, __dmul_rn(2.0, k2)), MM2);
+    const double e = __dmul_rn(D1, Mm);
+    const double D2 = __dadd_rn(__dadd_rn(__dadd_rn(a, b), c), -e);
+    const double g = __dmul_rn(__ddiv_rn(-f, __dmul_rn(2.0, k2)), LL2);
+    return __dadd_rn(__dadd_rn(g, __dmul_rn(D1, L)), D2);
+}
+
+// ---------------------------------------------------------------------------------------
+// Gaussian log-posterior (classes_SAMPLER.py:295-316); constants in shared memory.
+// ---------------------------------------------------------------------------------------
+struct sdb_sproblem {
+    int d, m, prior_full, noise_full;
+    const double *prior_mean, *prior_scale, *obs, *noise_scale;  // smem
+    const int *prior_piv, *noise_piv;                            // smem
+};
+
+// -0.5 * v . C^{-1} v  with C given by its LU factors (row-major, unit lower) and LAPACK-style
+// pivots (row i was swapped with row piv[i], i = 0..n-1).  Loops are written over the compile-time
+// bound N so that for small N everything stays in registers.
+template <int N>
+__device__ __forceinline__ double sdb_quad_lu(const double *lu, const int *piv, int n, const double *v) {
+    constexpr int UN = (N <= 4) ? N : 1;
+    double b[N];
+#pragma unroll UN
+    for (int i = 0; i < N; ++i)
+        if (i < n) b[i] = v[i];
+#pragma unroll UN
+    for (int i = 0; i < N; ++i)
+        if (i < n) {
+            const int p = piv[i];
+#pragma unroll UN
+            for (int q = 0; q < N; ++q)
+                if (q > i && q == p) { const double t = b[i]; b[i] = b[q]; b[q] = t; }
+        }
+#pragma unroll UN
+    for (int i = 1; i < N; ++i)            // L y = P v
+        if (i < n) {
+            double t = b[i];
+#pragma unroll UN
+            for (int j = 0; j < N; ++j)
+                if (j < i) t = __dadd_rn(t, -__dmul_rn(lu[i * n + j], b[j]));
+            b[i] = t;
+        }
+#pragma unroll UN
+    for (int ii = 0; ii < N; ++ii) {       // U x = y
+        const int i = N - 1 - ii;
+        if (i < n) {
+            double t = b[i];
+#pragma unroll UN
+            for (int j = 0; j < N; ++j)
+                if (j > i && j < n) t = __dadd_rn(t, -__dmul_rn(lu[i * n + j], b[j]));
+            b[i] = __ddiv_rn(t, lu[i * n + i]);
+        }
+    }
+    double q = 0.0;
+#pragma unroll UN
+    for (int i = 0; i < N; ++i)
+        if (i < n) q = __dadd_rn(q, __dmul_rn(v[i], b[i]));
+    return -0.5 * q;
+}
+
+template <int D, int M>
+__device__ __forceinline__ double sdb_log_posterior(const sdb_sproblem &p, const double *u, const double *G) {
+    constexpr int DD = D ? D : SDB_MAX_D;
+    constexpr int UD = D ? D : 1;  // unroll only the specialised sizes
+    constexpr int MM = M ? M : SDB_MAX_M;
+    constexpr int UM = M ? M : 1;
+    const int d = D ? D : p.d, m = M ? M : p.m;
+    double ll, lp;
+    {
+        double v[MM];
+#pragma unroll UM
+        for (int k = 0; k < MM; ++k)
+            if (k < m) v[k] = __dadd_rn(p.obs[k], -G[k]);
+        if (p.noise_full) {
+            ll = sdb_quad_lu<MM>(p.noise_scale, p.noise_piv, m, v);
+        } else {
+            double q = 0.0;
+#pragma unroll UM
+            for (int k = 0; k < MM; ++k)
+                if (k < m) q = __dadd_rn(q, __dmul_rn(v[k], __ddiv_rn(v[k], p.noise_scale[k])));
+            ll = -0.5 * q;
+        }
+    }
+    {
+        double v[DD];
+#pragma unroll UD
+        for (int j = 0; j < DD; ++j)
+            if (j < d) v[j] = __dadd_rn(u[j], -p.prior_mean[j]);
+        if (p.prior_full) {
+            lp = sdb_quad_lu<DD>(p.prior_scale, p.prior_piv, d, v);
+        } else {
+            double q = 0.0;
+#pragma unroll UD
+            for (int j = 0; j < DD; ++j)
+                if (j < d) q = __dadd_rn(q, __dmul_rn(v[j], __ddiv_rn(v[j], p.prior_scale[j])));
+            lp = -0.5 * q;
+        }
+    }
+    return __dadd_rn(ll, lp);
+}

@@ -1,0 +1,256 @@
+"""GPU parity tests of the surrogate update (refit) kernels through the C ABI: FP64 GEMM, LU with
+partial pivoting, the RBF saddle-point system, greedy thinning, MINRES, the polynomial normal
+equations + pinv solve -- against numpy / scipy, the numpy oracle and the golden vectors of the
+live reference.
+
+Tolerances: coefficients 1e-10 on well-conditioned fixtures; otherwise bounded by
+cond * eps (stated per test) together with evaluation parity on the training set and a residual no
+worse than the reference's.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import surrogate_poly as OP
+from oracle import surrogate_rbf as ORB
+from tests.golden_util import close, load
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from surrdamh_b200 import _lib
+    return _lib
+
+
+class Snap:
+    def __init__(self, sample, G_sample, weight=1):
+        self.sample, self.G_sample, self.weight = sample, G_sample, weight
+
+
+def test_dgemm_all_layouts(L):
+    rs = np.random.RandomState(0)
+    for (M, N, K) in ((1, 1, 1), (7, 5, 3), (128, 64, 8), (129, 65, 9), (300, 200, 1000), (21, 21, 5000), (3, 126, 777)):
+        A, B, C0 = rs.standard_normal((M, K)), rs.standard_normal((K, N)), rs.standard_normal((M, N))
+        want = 0.5 * C0 - 1.5 * A @ B
+        for a_t in (False, True):
+            for b_t in (False, True):
+                for nslab in (1, 4):
+                    # column-major storage == transposed row-major numpy arrays
+                    dA = L.dev(np.ascontiguousarray(A if a_t else A.T))   # a_t: row-major M x K (k fast) else column-major
+                    dB = L.dev(np.ascontiguousarray(B if b_t else B.T))
+                    dC = L.dev(np.ascontiguousarray(C0.T))
+                    sa = (K, 1) if a_t else (1, M)
+                    sb = (N, 1) if b_t else (1, K)
+                    ws = torch.empty((nslab * M * N + 1,), dtype=torch.float64, device="cuda")
+                    if nslab > 1:
+                        # split-K ignores beta inside the slabs and applies it in the reduction
+                        pass
+                    L.check(L.lib().sdb_dgemm(M, N, K, -1.5, L.ptr(dA), sa[0], sa[1], L.ptr(dB), sb[0], sb[1], 0.5, L.ptr(dC), M,
+                                              nslab, L.ptr(ws), L.stream_handle()))
+                    got = dC.cpu().numpy().T
+                    assert np.allclose(got, want, rtol=1e-12, atol=1e-12 * np.abs(want).max()), (M, N, K, a_t, b_t, nslab)
+
+
+def _lu_solve(L, A, B):
+    N = A.shape[0]
+    dA = L.dev(np.ascontiguousarray(A.T))          # column-major
+    dB = L.dev(np.ascontiguousarray(B.T))          # nrhs columns of length N
+    piv = torch.empty((N,), dtype=torch.int32, device="cuda")
+    info = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    L.check(L.lib().sdb_lu_solve(L.ptr(dA), N, L.ptr(dB), B.shape[1], L.ptr(piv), L.ptr(info), L.stream_handle()))
+    return dB.cpu().numpy().T, dA.cpu().numpy().T, piv.cpu().numpy(), int(info.item())
+
+
+@pytest.mark.parametrize("N", [1, 2, 7, 8, 9, 63, 64, 65, 130, 500, 1031, 2500, 4099, 8200])
+def test_lu_solve_matches_lapack(L, N):
+    import scipy.linalg
+    rs = np.random.RandomState(N)
+    A = rs.standard_normal((N, N))
+    B = rs.standard_normal((N, 3))
+    X, LU, piv, info = _lu_solve(L, A, B)
+    assert info == 0
+    lu_ref, piv_ref = scipy.linalg.lu_factor(A)
+    assert np.array_equal(piv, piv_ref)                         # same pivot sequence as dgetrf
+    assert np.allclose(LU, lu_ref, rtol=1e-9, atol=1e-9 * np.abs(lu_ref).max())
+    want = np.linalg.solve(A, B)
+    res = np.linalg.norm(A @ X - B) / (np.linalg.norm(A) * np.linalg.norm(X))
+    res_ref = np.linalg.norm(A @ want - B) / (np.linalg.norm(A) * np.linalg.norm(want))
+    assert res <= 10 * res_ref + 1e-16
+    cond = np.linalg.cond(A) if N <= 2500 else 1e6
+    assert np.linalg.norm(X - want) <= 50 * cond * 2.2e-16 * np.linalg.norm(want)
+
+
+def test_lu_singular_reports_info(L):
+    A = np.array([[1.0, 2.0, 3.0], [2.0, 4.0, 6.0], [1.0, 0.0, 1.0]])
+    A[:, 1] = 0.0
+    _, _, _, info = _lu_solve(L, A, np.ones((3, 1)))
+    assert info == 2                                          # U(1,1) == 0 (LAPACK numbering)
+
+
+def test_rbf_system_matches_oracle(L):
+    rs = np.random.RandomState(1)
+    for d, m, n, kt in ((4, 3, 160, 1), (2, 1, 77, 0), (3, 2, 50, 4), (3, 2, 50, 5), (2, 1, 33, 2), (2, 1, 33, 3), (2, 1, 33, 7)):
+        X, Y = rs.standard_normal((n, d)), rs.standard_normal((n, m))
+        up = ORB.RbfUpdate(d, m, kernel_type=kt, solver_type="direct")
+        up.add_arrays(X, Y)
+        up.update()
+        N = n + d + 1
+        S = torch.empty((N, N), dtype=torch.float64, device="cuda")
+        R = torch.empty((m, N), dtype=torch.float64, device="cuda")
+        L.check(L.lib().sdb_rbf_system(L.ptr(L.dev(X)), L.ptr(L.dev(Y)), n, d, m, kt, L.ptr(S), L.ptr(R), L.stream_handle()))
+        assert np.allclose(S.cpu().numpy(), up.last_system, rtol=1e-14, atol=0)
+        assert np.array_equal(R.cpu().numpy().T, up.last_rhs)
+        if kt in (0, 6):
+            assert np.array_equal(S.cpu().numpy(), up.last_system)      # distances themselves are bit-exact
+
+
+def test_rbf_update_golden(L):
+    """Surrogate_update with the reference's interface, two batches, every kernel type, thinning."""
+    from surrdamh_b200 import surrogate_rbf as SR
+    g = load("rbf")
+    X, Y = g["update_X"], g["update_Y"]
+    for i, (kt, minres, keep) in enumerate(g["update_cases"]):
+        up = SR.Surrogate_update(4, 3, kernel_type=int(kt), solver_type="minres" if minres else "direct",
+                                 no_keep=None if keep < 0 else int(keep))
+        up.add_data([Snap(X[j], Y[j]) for j in range(70)])
+        (CO1, C1), n1 = up.update()
+        up.add_data([Snap(X[j], Y[j]) for j in range(70, 160)])
+        (CO2, C2), n2 = up.update()
+        assert [n1, n2] == list(g[f"update{i}_n"]), i
+        assert np.array_equal(C1, g[f"update{i}_centers1"]) and np.array_equal(C2, g[f"update{i}_centers2"]), i
+        # cond(system) is 1e6..1e10 here: coefficients to 1e-5 (the bound the oracle itself is held to),
+        # evaluations on the training set far tighter for the direct solver
+        tol = 1e-4 if minres else 1e-5
+        assert close(CO1, g[f"update{i}_coefs1"], rtol=tol), (i, kt)
+        assert close(CO2, g[f"update{i}_coefs2"], rtol=tol), (i, kt)
+        if not minres:
+            ev = SR.Surrogate_apply(4, 3, kernel_type=int(kt))
+            got = ev.apply([CO2, C2], C2)
+            ref = ORB.RbfApply(4, 3, kernel_type=int(kt)).apply([g[f"update{i}_coefs2"], g[f"update{i}_centers2"]], C2)
+            assert close(got, ref, rtol=1e-8), (i, kt)
+
+
+def test_rbf_fit_residual_not_worse_than_lapack(L):
+    from surrdamh_b200 import surrogate_rbf as SR
+    rs = np.random.RandomState(7)
+    for d, m, n, kt in ((2, 1, 1500, 1), (4, 3, 900, 1), (8, 3, 700, 0), (4, 3, 600, 4)):
+        X = rs.standard_normal((n, d))
+        Y = np.stack([np.sin((k + 1) * X).sum(axis=1) for k in range(m)], axis=1)
+        up = SR.Surrogate_update(d, m, kernel_type=kt, solver_type="direct")
+        up.add_arrays(X, Y)
+        (CO, Cc), nn = up.update()
+        ref = ORB.RbfUpdate(d, m, kernel_type=kt, solver_type="direct")
+        ref.add_arrays(X, Y)
+        (COr, _), _ = ref.update()
+        S, R = ref.last_system, ref.last_rhs
+        res = np.linalg.norm(S @ CO - R) / (np.linalg.norm(S) * np.linalg.norm(CO))
+        res_ref = np.linalg.norm(S @ COr - R) / (np.linalg.norm(S) * np.linalg.norm(COr))
+        assert res <= 10 * res_ref + 1e-16, (d, m, n, kt, res, res_ref)
+        cond = np.linalg.cond(S)
+        assert np.linalg.norm(CO - COr) <= 50 * cond * 2.2e-16 * np.linalg.norm(COr), (d, m, n, kt, cond)
+
+
+def test_thinning_matches_oracle_including_ties(L):
+    rs = np.random.RandomState(2)
+    cases = []
+    cases.append((rs.standard_normal((300, 3)), 120))
+    grid = np.array([[i, j] for i in range(12) for j in range(12)], dtype=float)     # many exact ties
+    cases.append((grid, 60))
+    dup = rs.standard_normal((80, 2))
+    dup[10] = dup[3]; dup[50] = dup[3]; dup[77] = dup[20]                               # exact duplicates
+    cases.append((dup, 70))
+    cases.append((rs.standard_normal((1500, 4)), 1400))
+    cases.append((rs.standard_normal((40, 2)), 1))
+    for X, keep in cases:
+        n, d = X.shape
+        want = ORB.greedy_thinning(ORB.pairwise_distance(X, X), keep)
+        k = torch.empty((n,), dtype=torch.uint8, device="cuda")
+        w = torch.empty((L.lib().sdb_rbf_thin_work(n),), dtype=torch.float64, device="cuda")
+        L.check(L.lib().sdb_rbf_thin(L.ptr(L.dev(X)), n, d, keep, L.ptr(k), L.ptr(w), L.stream_handle()))
+        assert np.array_equal(k.cpu().numpy().astype(bool), want), (n, d, keep)
+
+
+def test_minres_matches_scipy(L):
+    import scipy.sparse.linalg as splin
+    rs = np.random.RandomState(3)
+    for n, d, kt in ((200, 4, 1), (600, 2, 1), (300, 3, 0)):
+        X, Y = rs.standard_normal((n, d)), rs.standard_normal((n, 1))
+        up = ORB.RbfUpdate(d, 1, kernel_type=kt, solver_type="direct")
+        up.add_arrays(X, Y)
+        up.update()
+        S, b = up.last_system, up.last_rhs[:, 0]
+        N = S.shape[0]
+        its = []
+        want, info_ref = splin.minres(S, b, rtol=1e-6, callback=lambda x: its.append(1))
+        x = torch.zeros((N,), dtype=torch.float64, device="cuda")
+        work = torch.empty((8 * N + 64,), dtype=torch.float64, device="cuda")
+        info = torch.zeros((4,), dtype=torch.int32, device="cuda")
+        L.check(L.lib().sdb_minres(L.ptr(L.dev(S)), N, L.ptr(L.dev(b)), None, L.ptr(x), 1e-6, 5 * N, L.ptr(work), L.ptr(info),
+                                   L.stream_handle()))
+        got, inf = x.cpu().numpy(), info.cpu().numpy()
+        assert inf[0] == info_ref
+        assert abs(int(inf[1]) - len(its)) <= max(2, len(its) // 50), (inf, len(its))     # same stopping rule
+        # both are the same unconverged Krylov iterate up to rounding drift
+        assert np.linalg.norm(got - want) <= 1e-3 * np.linalg.norm(want)
+        r_got, r_ref = np.linalg.norm(S @ got - b), np.linalg.norm(S @ want - b)
+        assert r_got <= 1.5 * r_ref + 1e-12
+
+
+def test_poly_fit_golden(L):
+    from surrdamh_b200 import surrogate_poly as SP
+    g = load("poly")
+    for i, (d, m, maxdeg, n1, n2, ill) in enumerate(g["update_cases"]):
+        X, Y = g[f"update{i}_X"], g[f"update{i}_Y"]
+        up = SP.Surrogate_update(int(d), int(m), max_degree=int(maxdeg))
+        up.add_data([Snap(X[j], Y[j]) for j in range(n1)])
+        (M1, deg1), c1 = up.update()
+        up.add_data([Snap(X[j], Y[j]) for j in range(n1, n1 + n2)])
+        (M2, deg2), c2 = up.update()
+        assert [deg1, deg2, c1, c2] == list(g[f"update{i}_deg"]), i
+        assert up.last_info[2] == 1                     # Jacobi converged
+        if not ill:
+            assert close(M1, g[f"update{i}_MAT1"], rtol=1e-10), i
+            assert close(M2, g[f"update{i}_MAT2"], rtol=1e-10), i
+        else:
+            # numerically rank-deficient normal matrix (cond ~1e13+): the truncated directions carry
+            # cond*eps noise in the coefficients; the fitted VALUES on the training set must agree
+            ev = OP.PolyApply(int(d), int(m))
+            v_got, v_ref = ev.apply([M2, int(deg2)], X), ev.apply([g[f"update{i}_MAT2"], int(deg2)], X)
+            assert np.abs(v_got - v_ref).max() <= 1e-4 * np.abs(v_ref).max()
+            r_got, r_ref = np.linalg.norm(v_got - Y), np.linalg.norm(v_ref - Y)
+            assert r_got <= 1.01 * r_ref + 1e-12
+
+
+def test_poly_basis_bit_exact(L):
+    import ctypes as C
+    from surrdamh_b200.device import DeviceModel
+    rs = np.random.RandomState(5)
+    for d, deg, n in ((2, 5, 1000), (4, 5, 300), (3, 3, 50), (6, 2, 20)):
+        X = rs.standard_normal((n, d)) * 1.4 + 0.3
+        alpha, herm = OP.multi_indices(d, deg), OP.hermite_table(deg)
+        want = OP.basis_matrix(herm, alpha, X)
+        mo = DeviceModel.poly(np.zeros((alpha.shape[0], 1)), deg, d)
+        PHI = torch.empty((n, alpha.shape[0]), dtype=torch.float64, device="cuda")
+        L.check(L.lib().sdb_poly_basis(L.ptr(L.dev(X)), n, d, C.byref(mo.struct), L.ptr(PHI), L.stream_handle()))
+        assert np.array_equal(PHI.cpu().numpy(), want), (d, deg)      # same operation order, no fma
+
+
+def test_poly_fit_large_well_conditioned(L):
+    from surrdamh_b200 import surrogate_poly as SP
+    rs = np.random.RandomState(6)
+    for d, m, deg, n in ((2, 1, 5, 200000), (4, 3, 5, 30000)):
+        X = rs.standard_normal((n, d))
+        Y = np.sin(X @ rs.standard_normal((d, m)))
+        up = SP.Surrogate_update(d, m, max_degree=deg)
+        up.add_arrays(X, Y)
+        (M, dg), cnt = up.update()
+        ref = OP.PolyUpdate(d, m, max_degree=deg)
+        ref.add_arrays(X, Y)
+        (Mr, dgr), _ = ref.update()
+        assert dg == dgr == deg and cnt == n
+        assert close(M, Mr, rtol=1e-10), (d, m)
