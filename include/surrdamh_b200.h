@@ -230,6 +230,8 @@ SDB_API int sdb_dgemm(int32_t M, int32_t N, int32_t K, double alpha, const doubl
                       double *d_ws, void *stream);
 
 /* ---- measurement ----------------------------------------------------------------------- */
+/* Number of kernels this library has launched in this process (reset != 0 zeroes the counter). */
+SDB_API int64_t sdb_launch_count(int32_t reset);
 /* FP64 FMA throughput probe (roofline denominator of the FP64-pipe-bound kernels):
  * FLOPs = blocks * 256 * 8 * 2 * iters.  d_out: DEVICE doubles [blocks * 256]. */
 SDB_API int sdb_fp64_probe(int64_t iters, int32_t blocks, double *d_out, void *stream);

@@ -443,6 +443,7 @@ extern "C" int sdb_chain_run(const sdb_chain_args *args, void *stream) {
     if (rc) return rc;
     chain_fn fn = pick_kernel(args->problem.d, args->problem.m);
     SDB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    sdb_count_launch();
     fn<<<blocks, threads, smem, (cudaStream_t)stream>>>(*args, L);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;

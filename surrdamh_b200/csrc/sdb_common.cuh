@@ -36,6 +36,8 @@ void sdb_set_error(const char *fmt, ...);
         }                                                                                  \
     } while (0)
 
+void sdb_count_launch();  // every kernel launch of the library is counted (sdb_launch_count)
+
 struct sdb_device_props {
     int sm_count, cc_major, cc_minor, smem_optin;
 };

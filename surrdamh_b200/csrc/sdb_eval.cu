@@ -56,6 +56,7 @@ extern "C" int sdb_poly_eval(const double *d_points, int64_t N, int32_t d, int32
     if (blocks > (int64_t)dp.sm_count * 16) blocks = (int64_t)dp.sm_count * 16;
     auto launch = [&](auto kern) -> int {
         SDB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sdb_count_launch();
         kern<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(d_points, N, d, m, *model, d_out);
         SDB_CUDA(cudaGetLastError());
         return SDB_OK;
@@ -198,6 +199,7 @@ extern "C" int sdb_rbf_eval(const double *d_points, int64_t N, int32_t d, int32_
                         2 * (sdb_align16((size_t)chunk * d * 8) + sdb_align16((size_t)chunk * m * 8));
     auto launch = [&](auto kern) -> int {
         SDB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sdb_count_launch();
         kern<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(d_points, N, d, m, *model, d_out, L, (int)chunk);
         SDB_CUDA(cudaGetLastError());
         return SDB_OK;

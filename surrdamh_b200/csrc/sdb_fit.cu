@@ -76,6 +76,7 @@ extern "C" int sdb_poly_basis(const double *d_points, int64_t N, int32_t d, cons
     if (blocks > (int64_t)dp.sm_count * 16) blocks = (int64_t)dp.sm_count * 16;
     auto launch = [&](auto kern) -> int {
         SDB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sdb_count_launch();
         kern<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(d_points, N, d, *model, d_PHI);
         SDB_CUDA(cudaGetLastError());
         return SDB_OK;
@@ -246,6 +247,7 @@ extern "C" int sdb_poly_fit(const double *d_X, const double *d_Y, int64_t n, int
     const size_t smem = use_smem ? need : 0;
     SDB_CUDA(cudaFuncSetAttribute((const void *)poly_pinv_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(use_smem ? need : 0)));
+    sdb_count_launch();
     poly_pinv_solve_kernel<<<1, 1024, smem, st>>>(A, RHS, P, m, d_MAT, Gg, use_smem, d_info);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
@@ -303,6 +305,7 @@ extern "C" int sdb_rbf_system(const double *d_X, const double *d_Y, int64_t n, i
     SDB_CHECK_ARG(kernel_type >= 0 && kernel_type <= 7, "sdb_rbf_system: kernel_type %d outside [0,7]", kernel_type);
     const int N = (int)n + d + 1;
     dim3 grid((N + 15) / 16, (N + 15) / 16);
+    sdb_count_launch();
     rbf_system_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_X, d_Y, (int)n, d, m, kernel_type, d_S, d_RHS);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
@@ -335,6 +338,7 @@ extern "C" int sdb_rbf_fit(const double *d_X, const double *d_Y, int64_t n, int3
     if (rc) return rc;
     int64_t blocks = (N * m + 255) / 256;
     if (blocks > 1184) blocks = 1184;
+    sdb_count_launch();
     transpose_out_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(RHS, (int)N, m, d_COEFS);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
@@ -458,7 +462,9 @@ extern "C" int sdb_rbf_thin(const double *d_X, int64_t n, int32_t d, int64_t no_
         SDB_CUDA(cudaMemsetAsync(d_keep, 1, (size_t)n, st));
         return SDB_OK;
     }
+    sdb_count_launch();
     thin_nearest_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(d_X, (int)n, d, nn_dist, nn_idx);
+    sdb_count_launch();
     thin_remove_kernel<<<1, 1024, 0, st>>>(d_X, (int)n, d, (int)no_keep, nn_dist, nn_idx, d_keep);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;

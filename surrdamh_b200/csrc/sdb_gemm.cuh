@@ -161,12 +161,15 @@ static inline int sdb_gemm(cudaStream_t st, int M, int N, int K, double alpha, c
     dim3 grid((M + GM_BM - 1) / GM_BM, (N + GM_BN - 1) / GM_BN, nslab);
     if (nslab == 1) {
         g.C = C; g.ldc = ldc; g.c_slab = 0;
+        sdb_count_launch();
         sdb_gemm_kernel<<<grid, 256, 0, st>>>(g);
     } else {
         g.C = slab_ws; g.ldc = M; g.c_slab = (int64_t)M * N;
+        sdb_count_launch();
         sdb_gemm_kernel<<<grid, 256, 0, st>>>(g);
         int64_t blocks = ((int64_t)M * N + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
+        sdb_count_launch();
         sdb_gemm_reduce<<<(unsigned)blocks, 256, 0, st>>>(C, ldc, slab_ws, (int64_t)M * N, M, M, N, nslab, beta);
     }
     SDB_CUDA(cudaGetLastError());

@@ -230,10 +230,10 @@ __global__ void __launch_bounds__(128) lu_trsm_lunit_kernel(const double *__rest
 static int lu_trsm_lunit(cudaStream_t st, const double *Lp, int64_t ldl, double *B, int64_t ldb, int h, int ncols) {
     if (ncols <= 0 || h <= 0) return SDB_OK;
     const int blocks = (ncols + 127) / 128;
-    if (h <= 8) lu_trsm_lunit_kernel<8><<<blocks, 128, 0, st>>>(Lp, ldl, B, ldb, h, ncols);
-    else if (h <= 16) lu_trsm_lunit_kernel<16><<<blocks, 128, 0, st>>>(Lp, ldl, B, ldb, h, ncols);
-    else if (h <= 32) lu_trsm_lunit_kernel<32><<<blocks, 128, 0, st>>>(Lp, ldl, B, ldb, h, ncols);
-    else lu_trsm_lunit_kernel<64><<<blocks, 128, 0, st>>>(Lp, ldl, B, ldb, h, ncols);
+    if (h <= 8) { sdb_count_launch(); lu_trsm_lunit_kernel<8><<<blocks, 128, 0, st>>>(Lp, ldl, B, ldb, h, ncols); }
+    else if (h <= 16) { sdb_count_launch(); lu_trsm_lunit_kernel<16><<<blocks, 128, 0, st>>>(Lp, ldl, B, ldb, h, ncols); }
+    else if (h <= 32) { sdb_count_launch(); lu_trsm_lunit_kernel<32><<<blocks, 128, 0, st>>>(Lp, ldl, B, ldb, h, ncols); }
+    else { sdb_count_launch(); lu_trsm_lunit_kernel<64><<<blocks, 128, 0, st>>>(Lp, ldl, B, ldb, h, ncols); }
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
 }
@@ -241,11 +241,11 @@ static int lu_trsm_lunit(cudaStream_t st, const double *Lp, int64_t ldl, double 
 static int lu_base(cudaStream_t st, double *A, int64_t lda, int N, int j0, int w, int *piv, int *info) {
     const int rows = N - j0;
     const int per = (rows + LU_CL * LU_T - 1) / (LU_CL * LU_T);
-    if (per <= 1) lu_base_kernel<1><<<LU_CL, LU_T, 0, st>>>(A, lda, N, j0, w, piv, info);
-    else if (per <= 2) lu_base_kernel<2><<<LU_CL, LU_T, 0, st>>>(A, lda, N, j0, w, piv, info);
-    else if (per <= 4) lu_base_kernel<4><<<LU_CL, LU_T, 0, st>>>(A, lda, N, j0, w, piv, info);
-    else if (per <= 8) lu_base_kernel<8><<<LU_CL, LU_T, 0, st>>>(A, lda, N, j0, w, piv, info);
-    else if (per <= 12) lu_base_kernel<12><<<LU_CL, LU_T, 0, st>>>(A, lda, N, j0, w, piv, info);
+    if (per <= 1) { sdb_count_launch(); lu_base_kernel<1><<<LU_CL, LU_T, 0, st>>>(A, lda, N, j0, w, piv, info); }
+    else if (per <= 2) { sdb_count_launch(); lu_base_kernel<2><<<LU_CL, LU_T, 0, st>>>(A, lda, N, j0, w, piv, info); }
+    else if (per <= 4) { sdb_count_launch(); lu_base_kernel<4><<<LU_CL, LU_T, 0, st>>>(A, lda, N, j0, w, piv, info); }
+    else if (per <= 8) { sdb_count_launch(); lu_base_kernel<8><<<LU_CL, LU_T, 0, st>>>(A, lda, N, j0, w, piv, info); }
+    else if (per <= 12) { sdb_count_launch(); lu_base_kernel<12><<<LU_CL, LU_T, 0, st>>>(A, lda, N, j0, w, piv, info); }
     else {
         sdb_set_error("sdb_lu: %d rows exceed the compiled limit of %d", rows, 12 * LU_CL * LU_T);
         return SDB_ERR_LIMIT;
@@ -261,6 +261,7 @@ static int lu_panel(cudaStream_t st, double *A, int64_t lda, int N, int j0, int 
     int rc = lu_panel(st, A, lda, N, j0, h, piv, info);
     if (rc) return rc;
     const int rcols = w - h;
+    sdb_count_launch();
     lu_laswp_kernel<<<(rcols + 127) / 128, 128, 0, st>>>(A, lda, j0 + h, j0 + w, piv, j0, j0 + h);
     double *A11 = A + (int64_t)j0 * lda + j0;
     double *A12 = A + (int64_t)(j0 + h) * lda + j0;
@@ -272,6 +273,7 @@ static int lu_panel(cudaStream_t st, double *A, int64_t lda, int N, int j0, int 
     if (rc) return rc;
     rc = lu_panel(st, A, lda, N, j0 + h, rcols, piv, info);
     if (rc) return rc;
+    sdb_count_launch();
     lu_laswp_kernel<<<(h + 127) / 128, 128, 0, st>>>(A, lda, j0, j0 + h, piv, j0 + h, j0 + w);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
@@ -282,9 +284,10 @@ static int lu_factor(cudaStream_t st, double *A, int64_t lda, int N, int *piv, i
         const int w = (N - j0) < LU_NB ? (N - j0) : LU_NB;
         int rc = lu_panel(st, A, lda, N, j0, w, piv, info);
         if (rc) return rc;
-        if (j0 > 0) lu_laswp_kernel<<<(j0 + 127) / 128, 128, 0, st>>>(A, lda, 0, j0, piv, j0, j0 + w);
+        if (j0 > 0) { sdb_count_launch(); lu_laswp_kernel<<<(j0 + 127) / 128, 128, 0, st>>>(A, lda, 0, j0, piv, j0, j0 + w); }
         const int rest = N - j0 - w;
         if (rest > 0) {
+            sdb_count_launch();
             lu_laswp_kernel<<<(rest + 127) / 128, 128, 0, st>>>(A, lda, j0 + w, N, piv, j0, j0 + w);
             double *A11 = A + (int64_t)j0 * lda + j0;
             double *A12 = A + (int64_t)(j0 + w) * lda + j0;
@@ -348,10 +351,12 @@ __global__ void __launch_bounds__(128) lu_apply_piv_rhs_kernel(double *__restric
 
 static int lu_solve_factored(cudaStream_t st, const double *A, int64_t lda, int N, const int *piv, double *B, int64_t ldb,
                              int nrhs) {
+    sdb_count_launch();
     lu_apply_piv_rhs_kernel<<<(nrhs + 127) / 128, 128, 0, st>>>(B, ldb, nrhs, piv, N);
     const int tb = (nrhs + 7) / 8;
     for (int k0 = 0; k0 < N; k0 += 64) {  // L y = P b
         const int h = (N - k0) < 64 ? (N - k0) : 64;
+        sdb_count_launch();
         lu_trsv_block_kernel<false><<<tb, 256, 0, st>>>(A, lda, B, ldb, k0, h, nrhs);
         const int rest = N - k0 - h;
         if (rest > 0) {
@@ -362,6 +367,7 @@ static int lu_solve_factored(cudaStream_t st, const double *A, int64_t lda, int 
     for (int k1 = N; k1 > 0;) {  // U x = y
         const int h = (k1 % 64) ? (k1 % 64) : 64;
         const int k0 = k1 - h;
+        sdb_count_launch();
         lu_trsv_block_kernel<true><<<tb, 256, 0, st>>>(A, lda, B, ldb, k0, h, nrhs);
         if (k0 > 0) {
             int rc = sdb_gemm(st, k0, nrhs, h, -1.0, A + (int64_t)k0 * lda, 1, lda, B + k0, 1, ldb, 1.0, B, ldb);

@@ -180,7 +180,8 @@ extern "C" int sdb_minres(const double *d_A, int64_t N, const double *d_b, const
     double *v = d_work, *y = v + N, *r1 = y + N, *r2 = r1 + N, *w = r2 + N, *w2 = w + N, *Av = w2 + N;
     minres_state *state = (minres_state *)(Av + N);
     const int mv_blocks = (n + 7) / 8;
-    if (d_x0) minres_matvec_kernel<<<mv_blocks, 256, 0, st>>>(d_A, n, d_x0, Av, nullptr);
+    if (d_x0) { sdb_count_launch(); minres_matvec_kernel<<<mv_blocks, 256, 0, st>>>(d_A, n, d_x0, Av, nullptr); }
+    sdb_count_launch();
     minres_init_kernel<<<1, 1024, 0, st>>>(n, d_b, d_x0 ? Av : nullptr, d_x0, d_x, v, y, r1, r2, w, w2, state);
     SDB_CUDA(cudaGetLastError());
     minres_state h;
@@ -191,7 +192,9 @@ extern "C" int sdb_minres(const double *d_A, int64_t N, const double *d_b, const
         SDB_CUDA(cudaStreamSynchronize(st));
         if (h.istop != 0 || done >= maxiter) break;
         for (int k = 0; k < chunk && done < maxiter; ++k, ++done) {
+            sdb_count_launch();
             minres_matvec_kernel<<<mv_blocks, 256, 0, st>>>(d_A, n, v, Av, state);
+            sdb_count_launch();
             minres_update_kernel<<<1, 1024, 0, st>>>(n, Av, d_x, v, y, r1, r2, w, w2, rtol, (int)maxiter, state);
         }
         SDB_CUDA(cudaGetLastError());
@@ -218,6 +221,7 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(int64_t iters, double *
 
 extern "C" int sdb_fp64_probe(int64_t iters, int32_t blocks, double *d_out, void *stream) {
     SDB_CHECK_ARG(iters >= 1 && blocks >= 1 && d_out, "sdb_fp64_probe: bad arguments");
+    sdb_count_launch();
     fp64_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, d_out);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;

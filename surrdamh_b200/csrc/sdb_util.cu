@@ -14,6 +14,14 @@ void sdb_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+static long long g_launches = 0;
+void sdb_count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
+extern "C" int64_t sdb_launch_count(int32_t reset) {
+    const long long v = __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
+    if (reset) __atomic_store_n(&g_launches, 0, __ATOMIC_RELAXED);
+    return v;
+}
+
 extern "C" const char *sdb_last_error(void) { return g_err; }
 extern "C" int sdb_abi_version(void) { return SDB_ABI_VERSION; }
 
@@ -77,6 +85,7 @@ extern "C" int sdb_philox_streams(uint64_t seed, uint32_t stream_id, int64_t cha
     const int64_t total = (int64_t)K * C;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
+    sdb_count_launch();
     philox_streams_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(seed, stream_id, chain0, step0, K, d, C, d_z, d_uni);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
@@ -94,6 +103,7 @@ extern "C" int sdb_philox_raw(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t 
     SDB_CHECK_ARG(n >= 1 && d_out, "sdb_philox_raw: n >= 1 and a destination are required");
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
+    sdb_count_launch();
     philox_raw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(seed, c0, c1, c2, c3, n, d_out);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
@@ -200,8 +210,11 @@ extern "C" int sdb_snapshot_compact(const uint8_t *d_flags, const double *d_snap
     const int64_t total = (int64_t)K * C;
     const int64_t nblocks = (total + CB - 1) / CB;
     cudaStream_t st = (cudaStream_t)stream;
+    sdb_count_launch();
     compact_count<<<(unsigned)nblocks, 256, 0, st>>>(d_flags, total, d_scratch);
+    sdb_count_launch();
     compact_scan<<<1, 1024, 0, st>>>(d_scratch, nblocks, d_count);
+    sdb_count_launch();
     compact_scatter<<<(unsigned)nblocks, 256, 0, st>>>(d_flags, d_snap_par, d_snap_obs, total, C, d, m, d_scratch, d_out_par,
                                                        d_out_obs, cap);
     SDB_CUDA(cudaGetLastError());

@@ -1,0 +1,190 @@
+"""The sampler stage loop for C lockstep chains per GPU.
+
+Host-side counterpart of surrDAMH/process_SAMPLER.py:25-88 (build problem / proposal / proxies, initial
+samples, run the stages of `samplers_list` in order handing `current_sample` on) with the chain loop
+of classes_SAMPLER.py:147-220 executed by the fused CUDA kernel (csrc/sdb_chain.cu) for all chains
+at once, and the collector round-trip (process_COLLECTOR.py) reduced to Collector.exchange_and_refit.
+
+Two data paths per stage:
+  fused : the solver plugin offers device_model() -> K steps per kernel launch, G evaluated in-kernel
+  split : any other plugin (the reference's set_parameters / get_observations on the host) ->
+          per step: PROPOSE kernel, host G for the proposals that passed the surrogate test, DECIDE kernel
+Schedule (deterministic; SURVEY.md section 7 trap 7): in a stage with surrogate_is_updated the snapshots of every
+`refit_every` steps (and of the last, shorter block) are exchanged and the surrogate is refitted;
+the new model is used from the next step on.  A DAMH stage with no fitted surrogate is an error, as
+in the reference (trap 10) -- unless snapshots are already queued, in which case one refit is forced.
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .chains import ChainBlock, Proposal, Trace, compact_snapshots
+from .collector import Collector
+from .device import DeviceProblem
+from .lhs_normal import lhs_normal
+
+
+class StageResult:
+    def __init__(self, index, kind, steps, counters, seconds, refits):
+        self.index, self.kind, self.steps = index, kind, steps
+        self.counters = counters                    # [C][4] accepted, rejected, prerejected, rej_current
+        self.seconds, self.refits = seconds, refits
+
+    @property
+    def acceptance_rate(self):
+        return self.counters[:, 0] / np.maximum(1, self.steps)
+
+    def summary(self):
+        acc, rej, pre = [int(v) for v in self.counters[:, :3].sum(axis=0)]
+        return dict(stage=self.index, type=self.kind, steps=self.steps, chains=int(self.counters.shape[0]), accepted=acc,
+                    rejected=rej, prerejected=pre, seconds=self.seconds, refits=self.refits)
+
+
+class LockstepSampler:
+    def __init__(self, conf, no_chains=None, rank=0, world=1, group=None, device=None, solver=None, trace_sink=None,
+                 streams=None, moments=False):
+        """conf: surrdamh_b200.configuration.Configuration.  no_chains: chains of THIS rank (default
+        conf.no_chains).  streams: optional callable (stage, step0, K) -> (z [K][d][C], uni [K][2][C]) device
+        tensors replacing Philox (parity runs).  trace_sink: optional callable (stage_index, step0, K, Trace)
+        receiving the per-step trace of every launch (CSV writer, tests)."""
+        L.require_cuda()
+        self.conf = conf
+        self.rank, self.world, self.group = rank, world, group
+        self.device = torch.device(device or "cuda")
+        self.C = int(no_chains if no_chains is not None else conf.no_chains)
+        self.d, self.m = conf.no_parameters, conf.no_observations
+        pp = conf.problem_parameters
+        self.problem = DeviceProblem(self.d, prior_mean=pp["prior_mean"], prior_std=pp["prior_std"], noise_std=pp["noise_std"],
+                                     no_observations=self.m, observations=pp["observations"], device=self.device)
+        self.solver = solver if solver is not None else conf.child_solver_init(**conf.child_solver_parameters)
+        self.truth = None
+        if conf.device_solver and hasattr(self.solver, "device_model"):
+            self.truth = self.solver.device_model()
+        self.trace_sink, self.streams = trace_sink, streams
+        self.chain0 = rank * self.C                               # global index of this rank's first chain
+        self.block = ChainBlock(self.problem, self.C, initial=self._initial_samples(), chain0=self.chain0, seed=conf.seed,
+                                moments=moments, device=self.device)
+        self.collector = None
+        if conf.use_surrogate:
+            kt = conf.surr_updater_parameters.get("kernel_type", 0) if conf.surrogate_type == "rbf" else 0
+            self.apply_kernel_type = conf.surr_solver_parameters.get("kernel_type", 0) if conf.surrogate_type == "rbf" else 0
+            updater = None
+            if world == 1 or rank == 0 or conf.refit_mode == "replicated":
+                kw = {k: v for k, v in conf.surr_updater_parameters.items() if k not in ("no_parameters", "no_observations")}
+                updater = conf.surr_updater_init(self.d, self.m, **kw)
+            self.collector = Collector(updater, conf.surrogate_type, self.d, self.m, kernel_type=self.apply_kernel_type,
+                                       group=group, rank=rank, world=world, snapshots_per_refit=conf.snapshots_per_refit,
+                                       refit_mode=conf.refit_mode, device=self.device)
+        self.global_step = 0
+        self.results = []
+        self.no_G_calls_host = 0
+
+    # process_SAMPLER.py:48-52 -- LHS rows `rank` of an N-point design, or the prior mean
+    def _initial_samples(self):
+        if self.conf.initial_sample_type == "lhs":
+            total = self.C * self.world      # the reference's O(n^2) memory is avoided, any chain count works
+            pp = self.conf.problem_parameters
+            pts = lhs_normal(self.d, pp["prior_mean"], pp["prior_std"], total, 0)
+            return pts[self.rank * self.C:(self.rank + 1) * self.C]
+        return None
+
+    # ---- one stage -------------------------------------------------------------------------------------
+    def _proposal(self, st):
+        if st.get("proposal_differs", False):
+            per = st["proposal_std"][self.chain0:self.chain0 + self.C]
+            return Proposal(self.d, per, per_chain=True, device=self.device)
+        return Proposal(self.d, st["proposal_std"], device=self.device)
+
+    def _host_G(self, params):
+        out = np.empty((params.shape[0], self.m))
+        for i, p in enumerate(params):
+            self.solver.set_parameters(p)
+            out[i] = np.asarray(self.solver.get_observations(), dtype=float).reshape(-1)
+        self.no_G_calls_host += params.shape[0]
+        return out
+
+    def run_stage(self, i, st, timed_refit=False):
+        kind, n_steps = st["type"], int(st["max_samples"])
+        time_limit = float(st.get("time_limit", float("inf")))
+        blk, col = self.block, self.collector
+        collects = col is not None and st["surrogate_is_updated"] is True
+        prop = self._proposal(st)
+        if "initial_sample" in st:
+            blk.set_current(st["initial_sample"])
+        blk.reset_counters()
+        blk.stream_id = i                                   # a fresh acceptance / proposal sub-stream per stage (seed0+2+i there)
+        surrogate = col.model if (col is not None and kind == "DAMH") else None
+        if kind == "DAMH" and surrogate is None:
+            raise TypeError("cannot unpack non-iterable NoneType object: DAMH stage %d starts before any surrogate was "
+                            "fitted (the reference fails the same way; run an MH stage with surrogate_is_updated first)" % i)
+        t0 = time.time()
+        if self.truth is not None:
+            blk.prepare(kind, surrogate, self.truth)
+        else:
+            blk.prepare(kind, surrogate, None, G_host=self._host_G(blk.current_numpy()))
+        R = self.conf.refit_every if collects else min(n_steps, 1024)
+        refits0 = col.no_refits if col is not None else 0
+        done, swapped = 0, False
+        trace = None
+        while done < n_steps:
+            K = min(R, n_steps - done)
+            need_trace = collects or self.trace_sink is not None
+            if need_trace and (trace is None or trace.K < K):
+                trace = Trace(K, self.C, self.d, self.m, self.device, snapshots=collects, full=self.trace_sink is not None or self.truth is None)
+            strm = None if self.streams is None else self.streams(i, done, K)
+            if self.truth is not None:
+                blk.run(kind, K, prop, surrogate, self.truth, trace=trace if need_trace else None, streams=strm, refresh_pre=swapped)
+            else:
+                self._run_split(kind, K, prop, surrogate, trace, strm, swapped, collects)
+            swapped = False
+            if self.trace_sink is not None:
+                self.trace_sink(i, done, K, trace)
+            done += K
+            self.global_step += K
+            if collects:
+                par, obs, cnt = compact_snapshots(trace, K, self._snapshot_capacity(K))
+                if col.exchange_and_refit(par, obs, cnt, self.global_step, timed=timed_refit):
+                    if kind == "DAMH":
+                        surrogate, swapped = col.model, True
+            if time.time() - t0 > time_limit:
+                break
+        torch.cuda.synchronize(self.device)
+        res = StageResult(i, kind, done, blk.counters_numpy(), time.time() - t0, (col.no_refits - refits0) if col is not None else 0)
+        self.results.append(res)
+        return res
+
+    def _snapshot_capacity(self, K):
+        cap = K * self.C
+        if self.collector.cap is not None:
+            cap = min(cap, self.collector.cap)
+        return cap
+
+    def _run_split(self, kind, K, prop, surrogate, trace, strm, swapped, collects):
+        """K steps with the true model evaluated by the host plugin (one step per kernel pair)."""
+        blk = self.block
+        one = Trace(1, self.C, self.d, self.m, self.device, snapshots=collects)
+        for k in range(K):
+            st = None if strm is None else (strm[0][k:k + 1].contiguous(), strm[1][k:k + 1].contiguous())
+            blk.propose(kind, prop, surrogate, one, streams=st, refresh_pre=swapped and k == 0)
+            flags = one.flags[0].cpu().numpy()
+            idx = np.nonzero(flags == L.FLAG_PENDING)[0]
+            G = np.zeros((self.C, self.m))
+            if idx.size:
+                props = one.prop[0].cpu().numpy().T
+                G[idx] = self._host_G(props[idx])
+            Gd = L.dev(np.ascontiguousarray(G.T), device=self.device)
+            blk.decide(kind, prop, surrogate, one, Gd, streams=st)
+            if trace is not None:
+                trace.flags[k] = one.flags[0]
+                if trace.prop is not None:
+                    trace.prop[k], trace.post[k], trace.pre[k] = one.prop[0], one.post[0], one.pre[0]
+                if collects:
+                    trace.snap_par[k], trace.snap_obs[k] = one.snap_par[0], one.snap_obs[0]
+
+    def run(self, timed_refit=False):
+        """All stages of samplers_list (process_SAMPLER.py:53-88)."""
+        for i, st in enumerate(self.conf.list_alg):
+            self.run_stage(i, st, timed_refit=timed_refit)
+        return self.results

@@ -52,6 +52,8 @@ class Surrogate_apply:
         pts, was_numpy = _points(datapoints, self.no_parameters)
         N = pts.shape[0]
         out = torch.empty((N, self.no_observations), dtype=torch.float64, device=pts.device)
+        if N == 0:
+            return out.cpu().numpy() if was_numpy else out
         L.check(L.lib().sdb_poly_eval(L.ptr(pts), N, self.no_parameters, self.no_observations, C.byref(mo.struct),
                                       L.ptr(out), L.stream_handle(stream)))
         return out.cpu().numpy() if was_numpy else out
