@@ -224,7 +224,7 @@ def run_ours(args):
 
     # ---- CPU baseline (rank 0, N == 1 only), before the timed GPU region -------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile:
         cpu = cpu_baseline(args.workload, SOL0, truth_SOL, args.cpu_seconds)
 
     prob = DeviceProblem(d, **w["problem"], device=dev)
@@ -290,6 +290,16 @@ def run_ours(args):
     blk.prepare("DAMH", sur, truth)
     for _ in range(max(args.warmup, 3)):
         one_block(False)
+    if args.profile:
+        # one bench step between cudaProfilerStart/Stop (ncu --profile-from-start off); nothing is reported
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        for _ in range(args.profile):
+            one_block(False)
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profile_blocks": args.profile, "note": "no measurement taken in profile mode"}))
+        return
     # ---- FP64 peak probe (roofline denominator), live ---------------------------------------------------
     info = L.device_info()
     pb, iters = info["sm_count"] * 8, 20000
@@ -437,11 +447,18 @@ def main():
     ap.add_argument("--centers", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", type=int, default=0, help="run this many bench steps inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        import torch
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        # a non-default stream: kernels, events and NCCL calls all go to it; the legacy default stream
+        # could not be captured into the refit's CUDA graph
+        with torch.cuda.stream(torch.cuda.Stream(device=local)):
+            run_ours(args)
 
 
 if __name__ == "__main__":

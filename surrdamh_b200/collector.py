@@ -35,6 +35,7 @@ class Collector:
         self.history = []                       # (global_step, snapshots used by the refit)
         self.refit_ms = []
         self.model_factory = self._device_model   # (kind, coefs, centers | degree) -> model; tests stub it on CPU
+        self.refit_hook = None                    # optional (par_all, obs_all, refit_index) -> SOL: replaces the fit (parity runs)
 
     def _device_model(self, kind, coefs, extra):
         if kind == "rbf":
@@ -99,6 +100,12 @@ class Collector:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
         model = None
+        if self.refit_hook is not None:
+            SOL = self.refit_hook(par_all, obs_all, self.no_refits)
+            self.model = self.model_factory(self.surrogate_type, SOL[0], SOL[1])
+            self.no_refits += 1
+            self.history.append((global_step, int(par_all.shape[0])))
+            return True
         if self.world == 1 or self.refit_mode == "replicated" or self.rank == 0:
             self.updater.add_arrays(par_all, obs_all)
             model, n = self.updater.update_device()

@@ -37,6 +37,7 @@ void sdb_set_error(const char *fmt, ...);
     } while (0)
 
 void sdb_count_launch();  // every kernel launch of the library is counted (sdb_launch_count)
+extern "C" SDB_API int64_t sdb_launch_count(int32_t reset);
 
 struct sdb_device_props {
     int sm_count, cc_major, cc_minor, smem_optin;
@@ -152,22 +153,22 @@ __device__ __forceinline__ void sdb_bulk_stage(void *smem_dst, const void *gmem_
 // ---------------------------------------------------------------------------------------
 // small math
 // ---------------------------------------------------------------------------------------
-// sqrt for the pair loops: MUFU.RSQ64H seed + two coupled Goldschmidt steps (7 DFMA-class
-// ops, no special-case branches; relative error ~1 ulp).  s == 0 yields exactly 0.
-__device__ __forceinline__ double sdb_fast_sqrt(double s) {
+// 1/sqrt(s) for the pair loops: MUFU.RSQ64H seed (relative error e ~ 2^-22) + ONE third-order
+// correction y (1 + e/2 + 3 e^2/8), e = 1 - s y^2 -- five FP64-pipe operations, error ~ e^3, i.e. the
+// result is rounded-to-nearest quality.  The s == 0 / subnormal guard is an integer test on the high word
+// (ALU pipe, not the FP64 pipe that bounds these loops); it yields 0, so s * rsqrt(s) = 0 without a NaN.
+__device__ __forceinline__ double sdb_fast_rsqrt(double s) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
-    // guard s == 0 (y = inf) and denormal-scale s without a branch: clamp the seed
-    y = (s > 1e-300) ? y : 0.0;
-    double g = s * y;       // ~ sqrt(s)
-    double h = 0.5 * y;     // ~ 1/(2 sqrt(s))
-    double e = fma(-g, h, 0.5);
-    g = fma(g, e, g);
-    h = fma(h, e, h);
-    e = fma(-g, h, 0.5);
-    g = fma(g, e, g);
-    return g;
+    const int hi = __double2hiint(s);
+    y = __hiloint2double(hi < 0x00100000 ? 0 : __double2hiint(y), 0);   // RSQ64H fills the high word only
+    const double t = s * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double q = e * p;
+    return fma(y, q, y);
 }
+__device__ __forceinline__ double sdb_fast_sqrt(double s) { return s * sdb_fast_rsqrt(s); }
 
 __device__ __forceinline__ double sdb_shfl_xor(double v, int lanemask, unsigned mask = 0xffffffffu) {
     return __shfl_xor_sync(mask, v, lanemask);
@@ -184,7 +185,7 @@ __device__ __forceinline__ double sdb_rbf_phi(double s, int kernel_type) {
         case 3: { const double r = sdb_fast_sqrt(s); return s * s * s * r; }    // r^7
         case 7: { const double r = sdb_fast_sqrt(s); const double s2 = s * s; return s2 * s2 * r; }  // r^9
         case 4: return exp(-s);                                                  // exp(-r^2)
-        case 5: return rsqrt(s + 1.0);                                           // (r^2+1)^(-1/2)
+        case 5: return sdb_fast_rsqrt(s + 1.0);                                  // (r^2+1)^(-1/2)
         default: return sdb_fast_sqrt(s);                                        // 0 and 6: r
     }
 }

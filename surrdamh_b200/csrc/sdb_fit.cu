@@ -375,76 +375,90 @@ __global__ void __launch_bounds__(256) thin_nearest_kernel(const double *__restr
     if (lane == 0) { nn_dist[row] = best; nn_idx[row] = bj; }
 }
 
-__global__ void __launch_bounds__(1024, 1) thin_remove_kernel(const double *__restrict__ X, int n, int d, int no_keep,
-                                                              double *__restrict__ nn_dist, int *__restrict__ nn_idx,
-                                                              uint8_t *__restrict__ keep) {
+// (distance, index) arg-min over the block, ties -> smallest index; result broadcast to all threads.
+__device__ __forceinline__ void block_argmin(double &best, int &bidx, double *rv, int *rr) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+        if (ov < best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+    __syncthreads();  // previous readers of rv / rr are done
+    if (lane == 0) { rv[warp] = best; rr[warp] = bidx; }
+    __syncthreads();
+    best = rv[lane]; bidx = rr[lane];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+        if (ov < best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+}
+
+// The removal loop, one CTA.  When they fit, the points and the three per-point arrays are staged in
+// shared memory (use_smem), so an iteration costs a handful of barriers instead of L2 round trips.
+__global__ void __launch_bounds__(1024, 1) thin_remove_kernel(const double *__restrict__ Xg, int n, int d, int no_keep,
+                                                              double *__restrict__ nn_dist_g, int *__restrict__ nn_idx_g,
+                                                              uint8_t *__restrict__ keep_g, int use_smem) {
+    extern __shared__ __align__(16) unsigned char thin_sm[];
     __shared__ double rv[32];
     __shared__ int rr[32];
-    __shared__ int victim;
     __shared__ int todo[1024];
     __shared__ int ntodo;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
+    const double *X = Xg;
+    double *nn_dist = nn_dist_g;
+    int *nn_idx = nn_idx_g;
+    uint8_t *keep = keep_g;
+    if (use_smem) {
+        double *Xs = (double *)thin_sm;
+        nn_dist = Xs + (size_t)n * d;
+        nn_idx = (int *)(nn_dist + n);
+        keep = (uint8_t *)(nn_idx + n);
+        for (int e = tid; e < n * d; e += blockDim.x) Xs[e] = Xg[e];
+        for (int i = tid; i < n; i += blockDim.x) { nn_dist[i] = nn_dist_g[i]; nn_idx[i] = nn_idx_g[i]; }
+        X = Xs;
+    }
     for (int i = tid; i < n; i += blockDim.x) keep[i] = 1;
+    if (tid == 0) ntodo = 0;
     __syncthreads();
     for (int it = 0; it < n - no_keep; ++it) {
-        // global minimum over alive rows; ties -> smallest row
+        // global minimum over alive rows; ties -> smallest row (= the first flat arg-min of the reference)
         double best = DBL_MAX;
         int brow = INT_MAX;
         for (int i = tid; i < n; i += blockDim.x)
             if (keep[i] && nn_idx[i] != INT_MAX && nn_dist[i] < best) { best = nn_dist[i]; brow = i; }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, best, off);
-            const int orow = __shfl_xor_sync(0xffffffffu, brow, off);
-            if (ov < best || (ov == best && orow < brow)) { best = ov; brow = orow; }
-        }
-        if (lane == 0) { rv[warp] = best; rr[warp] = brow; }
-        __syncthreads();
-        if (warp == 0) {
-            best = rv[lane]; brow = rr[lane];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, best, off);
-                const int orow = __shfl_xor_sync(0xffffffffu, brow, off);
-                if (ov < best || (ov == best && orow < brow)) { best = ov; brow = orow; }
-            }
-            if (lane == 0) { victim = brow; ntodo = 0; }
-        }
-        __syncthreads();
-        const int v = victim;
+        block_argmin(best, brow, rv, rr);
+        const int v = brow;
         if (v == INT_MAX) break;  // fewer than two alive points
         if (tid == 0) keep[v] = 0;
-        __syncthreads();
         // rows whose nearest neighbour was the victim must be rescanned
         for (int base = 0; base < n; base += 1024) {
             const int i = base + tid;
-            if (i < n && keep[i] && nn_idx[i] == v) {
-                const int slot = atomicAdd(&ntodo, 1);
-                todo[slot] = i;   // at most 1024 per chunk
-            }
+            if (i < n && i != v && keep[i] && nn_idx[i] == v) todo[atomicAdd(&ntodo, 1)] = i;   // at most 1024 per chunk
             __syncthreads();
             const int cnt = ntodo;
-            for (int t = warp; t < cnt; t += 32) {
+            for (int t = 0; t < cnt; ++t) {   // the whole CTA scans one row at a time
                 const int row = todo[t];
                 double b = DBL_MAX;
                 int bj = INT_MAX;
-                for (int j = lane; j < n; j += 32) {
+                for (int j = tid; j < n; j += blockDim.x) {
                     if (j == row || !keep[j]) continue;
                     const double r = ref_distance(X + (size_t)row * d, X + (size_t)j * d, d);
                     if (r < b) { b = r; bj = j; }
                 }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double ov = __shfl_xor_sync(0xffffffffu, b, off);
-                    const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
-                    if (ov < b || (ov == b && oj < bj)) { b = ov; bj = oj; }
-                }
-                if (lane == 0) { nn_dist[row] = b; nn_idx[row] = bj; }
+                block_argmin(b, bj, rv, rr);
+                if (tid == 0) { nn_dist[row] = b; nn_idx[row] = bj; }
             }
             __syncthreads();
             if (tid == 0) ntodo = 0;
-            __syncthreads();
         }
+        __syncthreads();
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = tid; i < n; i += blockDim.x) keep_g[i] = keep[i];
     }
 }
 
@@ -464,8 +478,15 @@ extern "C" int sdb_rbf_thin(const double *d_X, int64_t n, int32_t d, int64_t no_
     }
     sdb_count_launch();
     thin_nearest_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(d_X, (int)n, d, nn_dist, nn_idx);
+    sdb_device_props dp;
+    int rc = sdb_get_device_props(&dp);
+    if (rc) return rc;
+    const size_t need = (size_t)n * ((size_t)d * 8 + 8 + 4 + 1) + 16;
+    const int use_smem = need + 8192 <= (size_t)dp.smem_optin;
+    SDB_CUDA(cudaFuncSetAttribute((const void *)thin_remove_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(use_smem ? need : 0)));
     sdb_count_launch();
-    thin_remove_kernel<<<1, 1024, 0, st>>>(d_X, (int)n, d, (int)no_keep, nn_dist, nn_idx, d_keep);
+    thin_remove_kernel<<<1, 1024, use_smem ? need : 0, st>>>(d_X, (int)n, d, (int)no_keep, nn_dist, nn_idx, d_keep, use_smem);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
 }

@@ -175,3 +175,107 @@ static inline int sdb_gemm(cudaStream_t st, int M, int N, int K, double alpha, c
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------
+// Rank-K update with K <= 64, the LU trailing update:  C[M x N] -= A[M x K] * B[K x N], all column-major
+// with a common leading dimension (A m-contiguous, B k-contiguous).  The whole K extent of a 128 x 64
+// tile is brought into shared memory by cp.async (8-byte pieces: lda may be odd, so 16-byte alignment is
+// not guaranteed) in two halves, so the second half loads while the first is multiplied; no other barrier.
+// ---------------------------------------------------------------------------------------------------
+#define GK_K 64
+#define GK_APAD 8
+#define GK_BPAD 4   // Bs is [n][k]: row stride 68 doubles == 4 (mod 16): the 8 n-rows of a fragment load spread over all banks
+
+__device__ __forceinline__ void sdb_cp_async8(void *smem, const void *gmem, bool pred) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    const int bytes = pred ? 8 : 0;   // src-size 0 -> zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+
+static __global__ void __launch_bounds__(256, 2) sdb_gemm_k64_kernel(const double *__restrict__ A, const double *__restrict__ B,
+                                                                     double *__restrict__ C, int64_t ld, int M, int N, int K) {
+    extern __shared__ __align__(16) double gk_sm[];
+    double (*As)[GM_BM + GK_APAD] = (double (*)[GM_BM + GK_APAD])gk_sm;                               // [64][136]
+    double (*Bs)[GK_K + GK_BPAD] = (double (*)[GK_K + GK_BPAD])(gk_sm + GK_K * (GM_BM + GK_APAD));     // [64 n][68]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+    const int m0 = blockIdx.x * GM_BM, n0 = blockIdx.y * GM_BN;
+    const int gid = lane >> 2, tig = lane & 3;
+    // two halves of K: rows [0,32) and [32,64) of As / Bs
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int kb = half * 32;
+        // A: 32 k-rows x 128 m  (4096 elements, 16 per thread), m fastest over threads
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int idx = tid + e * 256;
+            const int mm = idx & (GM_BM - 1), kk = kb + (idx >> 7);
+            const bool ok = (m0 + mm < M) && (kk < K);
+            sdb_cp_async8(&As[kk][mm], A + (int64_t)kk * ld + (m0 + mm), ok);
+        }
+        // B: 32 k x 64 n (2048 elements, 8 per thread), k fastest over threads (contiguous in memory)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int idx = tid + e * 256;
+            const int kk = kb + (idx & 31), nn = idx >> 5;
+            const bool ok = (n0 + nn < N) && (kk < K);
+            sdb_cp_async8(&Bs[nn][kk], B + (int64_t)(n0 + nn) * ld + kk, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        if (half == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (half * 32 < K) {
+#pragma unroll
+            for (int ks = 0; ks < 32; ks += 4) {
+                const int k = half * 32 + ks;
+                double fa[4], fb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) fa[i] = As[k + tig][wm + i * 8 + gid];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) fb[j] = Bs[wn + j * 8 + gid][k + tig];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sdb_dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gm = m0 + wm + i * 8 + gid, gn = n0 + wn + j * 8 + tig * 2 + e;
+                if (gm < M && gn < N) {
+                    double *p = C + (int64_t)gn * ld + gm;
+                    *p -= acc[i][j][e];
+                }
+            }
+}
+
+static inline int sdb_gemm_k64_update(cudaStream_t st, int M, int N, int K, const double *A, const double *B, double *C,
+                                      int64_t ld) {
+    if (M <= 0 || N <= 0 || K <= 0) return SDB_OK;
+    const int smem = (GK_K * (GM_BM + GK_APAD) + GM_BN * (GK_K + GK_BPAD)) * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SDB_CUDA(cudaFuncSetAttribute((const void *)sdb_gemm_k64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    dim3 grid((M + GM_BM - 1) / GM_BM, (N + GM_BN - 1) / GM_BN);
+    sdb_count_launch();
+    sdb_gemm_k64_kernel<<<grid, 256, smem, st>>>(A, B, C, ld, M, N, K);
+    SDB_CUDA(cudaGetLastError());
+    return SDB_OK;
+}

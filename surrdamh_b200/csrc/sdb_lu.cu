@@ -5,195 +5,293 @@
 // LAPACK conventions (unit lower L, pivot row indices piv[k] >= k applied in order).
 //
 //   * blocked right-looking outer loop, panel width LU_NB
-//   * inside a panel: recursive halving down to 8 columns; the 8-column base case keeps the whole
-//     (N - j) x 8 sub-panel in REGISTERS, spread over one thread-block cluster of 8 CTAs (8 SMs);
-//     per column one block-level arg-max, one exchange of the candidate rows through distributed
-//     shared memory and ONE cluster barrier
+//   * inside a panel: the (N - j) x w sub-panel is factored by ONE kernel that keeps it in the shared
+//     memory of a thread-block cluster of 16 CTAs (16 SMs); per column one block-level arg-max, one
+//     exchange of the candidate rows through distributed shared memory and ONE cluster barrier.  w is 64
+//     while the rows fit (N <= ~5800), else the panel is halved recursively (w = 32, 16, 8)
 //   * everything else (row interchanges, triangular solves with the 8..64-wide diagonal blocks,
 //     rank-k updates) runs on the whole GPU; the updates use the DMMA GEMM of sdb_gemm.cuh
 //   * solve phase: warp-per-right-hand-side triangular solves on 64 x 64 diagonal blocks + GEMM
 #include <cooperative_groups.h>
 #include <limits.h>
+#include <stdlib.h>
 
 #include "sdb_gemm.cuh"
 
 namespace cg = cooperative_groups;
 
-#define LU_CL 8    // CTAs per cluster (portable maximum)
 #define LU_T 512   // threads per CTA of the base case
 #define LU_W 8     // base-case width
 #define LU_NB 64   // outer panel width
 
-struct lu_cand {
-    double val;
-    int row;
-    int pad;
-    double vals[LU_W];
+// ---------------------------------------------------------------------------------------------------
+// Base case: factor the (N - j0) x w sub-panel (w <= W) starting at A(j0, j0); row interchanges are
+// applied to these w columns only.  The sub-panel lives in the SHARED MEMORY of one thread-block cluster
+// (CL = 8 or 16 CTAs): CTA `rank` holds rows [j0 + rank*rpc, j0 + (rank+1)*rpc) as tile[rpc][W+1].
+// Per column: block arg-max -> warp `r` of the winning CTA writes the candidate row (w values + |pivot| +
+// row index) into the mailbox of CTA r over distributed shared memory, the CTA holding the diagonal row
+// does the same with that row -> ONE cluster barrier -> every thread picks the global winner from its
+// own CTA's mailbox, the two owners swap their rows, every thread eliminates its rows.  Mailboxes are
+// double-buffered on the column parity.  Loops over columns are runtime loops: the code stays small
+// (the fully unrolled register variant of this kernel fell out of the instruction cache beyond 8 columns).
+// ---------------------------------------------------------------------------------------------------
+#define LU_CLMAX 16
+#ifdef SDB_LU_PROFILE
+__device__ long long g_lu_prof[8];
+#define LU_STAMP(k) do { const long long t_ = clock64(); t_acc[k] += t_ - t_last; t_last = t_; } while (0)
+#else
+#define LU_STAMP(k) do { } while (0)
+#endif
+template <int W>
+struct lu_mail {
+    double val[LU_CLMAX];
+    int row[LU_CLMAX];
+    double vals[LU_CLMAX][W];
 };
 
-// ---------------------------------------------------------------------------------------------------
-// Base case: factor the (N - j0) x w sub-panel (w <= 8) starting at A(j0, j0); row interchanges are
-// applied to these w columns only.  Row j0 + slot + q * 4096 lives in registers a[q][*] of thread `slot`.
-// ---------------------------------------------------------------------------------------------------
-template <int R>
-__global__ void __cluster_dims__(LU_CL, 1, 1) __launch_bounds__(LU_T, 1)
-    lu_base_kernel(double *__restrict__ A, int64_t lda, int N, int j0, int w, int *__restrict__ piv, int *__restrict__ info) {
+template <int W>
+__global__ void __launch_bounds__(LU_T, 1)
+    lu_base_kernel(double *__restrict__ A, int64_t lda, int N, int j0, int w, int rpc, int *__restrict__ piv, int *__restrict__ info) {
     cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (int)cluster.block_rank();
-    __shared__ lu_cand cand[2][LU_CL];
-    __shared__ double diag[2][LU_W];
+    const int rank = (int)cluster.block_rank(), CL = (int)cluster.num_blocks();
+    extern __shared__ __align__(16) double tile[];   // [rpc][W + 2], then int lrow[rpc], int done[rpc]
+    __shared__ lu_mail<W> mail[2];
+    __shared__ double rcp_s[W];
+    __shared__ int piv_s[W];
+    __shared__ int sing_s;
     __shared__ double red_val[LU_T / 32];
-    __shared__ int red_row[LU_T / 32];
+    __shared__ int red_row[LU_T / 32], red_slot[LU_T / 32];
     __shared__ double win_val;
-    __shared__ int win_row;
+    __shared__ int win_row, win_slot;
+    constexpr int TS = W + 2;                           // even: (row, even column) is 16-byte aligned; 33 i mod 8 banks
+    constexpr int CH = 16, NCH = (W + CH - 1) / CH;     // elimination work item = (row, 16-column chunk)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nslots = LU_CL * LU_T;
-    const int slot = rank * LU_T + tid;
+    const int row0 = j0 + rank * rpc;                       // first row of this CTA
+    const int nloc = max(0, min(rpc, N - row0));            // rows it really holds
+    int *lrow = (int *)(tile + (size_t)rpc * TS);           // logical row of every slot (rows are never moved)
+    int *done = lrow + rpc;                                 // column at which the slot became a pivot row (w: not yet)
 
-    double a[R][LU_W];
-#pragma unroll
-    for (int q = 0; q < R; ++q) {
-        const int row = j0 + slot + q * nslots;
-#pragma unroll
-        for (int c = 0; c < LU_W; ++c) a[q][c] = (row < N && c < w) ? A[(int64_t)(j0 + c) * lda + row] : 0.0;
-    }
+    for (int c = 0; c < w; ++c)
+        for (int i = tid; i < nloc; i += LU_T) tile[i * TS + c] = A[(int64_t)(j0 + c) * lda + row0 + i];
+    for (int i = tid; i < nloc; i += LU_T) { lrow[i] = row0 + i; done[i] = w; }
+    if (tid == 0) sing_s = 0;
+    __syncthreads();
 
-#pragma unroll
-    for (int c = 0; c < LU_W; ++c) {
-        if (c < w) {  // uniform over the whole cluster
-            const int buf = c & 1;
-            const int drow = j0 + c;
-            // ---- arg-max of |a(:, c)| over my rows >= drow (first maximum wins, as idamax) ------------
-            double best = -1.0;
-            int brow = INT_MAX;
-#pragma unroll
-            for (int q = 0; q < R; ++q) {
-                const int row = j0 + slot + q * nslots;
-                const double v = fabs(a[q][c]);
-                if (row < N && row >= drow && v > best) { best = v; brow = row; }
+#ifdef SDB_LU_PROFILE
+    long long t_acc[5] = {0, 0, 0, 0, 0};
+    long long t_last = clock64();
+#endif
+    int prow = -1, drow = -1, pcol = -1;   // the interchange of the previous column, applied by the slot owners
+    for (int c = 0; c < w; ++c) {
+        lu_mail<W> &mb = mail[c & 1];
+        LU_STAMP(0);
+        // ---- owners apply the previous interchange to their slots' logical rows, then scan column c ---------
+        double best = -1.0;
+        int brow = INT_MAX, bslot = -1;
+        for (int i = tid; i < nloc; i += LU_T) {
+            if (done[i] == w && pcol >= 0) {
+                const int lr = lrow[i];
+                if (lr == prow) { lrow[i] = drow; done[i] = pcol; }
+                else if (lr == drow) lrow[i] = prow;
             }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, best, off);
-                const int orow = __shfl_xor_sync(0xffffffffu, brow, off);
-                if (ov > best || (ov == best && orow < brow)) { best = ov; brow = orow; }
+            if (done[i] == w) {
+                const double v = fabs(tile[i * TS + c]);
+                const int lr = lrow[i];
+                if (v > best || (v == best && lr < brow)) { best = v; brow = lr; bslot = i; }
             }
-            if (lane == 0) { red_val[warp] = best; red_row[warp] = brow; }
-            __syncthreads();
-            if (warp == 0) {
-                double v = lane < LU_T / 32 ? red_val[lane] : -1.0;
-                int r = lane < LU_T / 32 ? red_row[lane] : INT_MAX;
+        }
+        drow = j0 + c;
 #pragma unroll
-                for (int off = 8; off > 0; off >>= 1) {
-                    const double ov = __shfl_xor_sync(0xffffffffu, v, off);
-                    const int orow = __shfl_xor_sync(0xffffffffu, r, off);
-                    if (ov > v || (ov == v && orow < r)) { v = ov; r = orow; }
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, off);
+            const int orow = __shfl_xor_sync(0xffffffffu, brow, off);
+            const int oslot = __shfl_xor_sync(0xffffffffu, bslot, off);
+            if (ov > best || (ov == best && orow < brow)) { best = ov; brow = orow; bslot = oslot; }
+        }
+        if (lane == 0) { red_val[warp] = best; red_row[warp] = brow; red_slot[warp] = bslot; }
+        __syncthreads();
+        if (warp == 0) {
+            double v = lane < LU_T / 32 ? red_val[lane] : -1.0;
+            int r = lane < LU_T / 32 ? red_row[lane] : INT_MAX;
+            int sl = lane < LU_T / 32 ? red_slot[lane] : -1;
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+                const int orow = __shfl_xor_sync(0xffffffffu, r, off);
+                const int oslot = __shfl_xor_sync(0xffffffffu, sl, off);
+                if (ov > v || (ov == v && orow < r)) { v = ov; r = orow; sl = oslot; }
+            }
+            if (lane == 0) { win_val = v; win_row = r; win_slot = sl; }
+        }
+        __syncthreads();
+        LU_STAMP(1);
+        // ---- publish: warp r writes this CTA's candidate row into the mailbox of CTA r ------------------------
+        if (warp < CL) {
+            lu_mail<W> *dst = cluster.map_shared_rank(&mb, warp);
+            const int wslot = win_slot;
+            if (wslot < 0) {
+                if (lane == 0) { dst->val[rank] = -1.0; dst->row[rank] = INT_MAX; }
+            } else {
+                const double *src = tile + (size_t)wslot * TS;
+                for (int k = lane; k < w; k += 32) dst->vals[rank][k] = src[k];
+                if (lane == 0) { dst->val[rank] = win_val; dst->row[rank] = win_row; }
+            }
+        }
+        LU_STAMP(2);
+        // cluster barrier with release / acquire at CLUSTER scope: orders the distributed-shared-memory writes
+        // above.  (cooperative_groups' cluster.sync() adds a GPU-scope MEMBAR and an L1 invalidate, ~1 us each.)
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        LU_STAMP(3);
+        // ---- every thread picks the global winner -----------------------------------------------------------
+        double pv = -1.0;
+        int pr = 0;
+        prow = INT_MAX;
+        for (int r = 0; r < CL; ++r) {
+            const double v = mb.val[r];
+            const int row = mb.row[r];
+            if (v > pv || (v == pv && row < prow)) { pv = v; prow = row; pr = r; }
+        }
+        const bool singular = !(pv > 0.0);  // exactly zero (or NaN) column: LAPACK records info and moves on
+        if (singular) prow = drow;
+        pcol = c;
+        const double *__restrict__ pvals = mb.vals[pr];
+        const double rcp = singular ? 1.0 : 1.0 / pvals[c];  // dgetf2 scales by the reciprocal
+        if (tid == 0) {   // kept in shared memory; global memory is not touched inside the column loop
+            rcp_s[c] = rcp;
+            piv_s[c] = prow;
+            if (singular && sing_s == 0) sing_s = drow + 1;
+        }
+        if (!singular) {
+            // rows still in play, except the new pivot row: a(i, c2) -= l_i * pivot(c2), l_i = a(i, c) / pivot(c).
+            // The scaling of column c itself is deferred to the write-back (nobody else reads it any more).
+            for (int it = tid; it < nloc * NCH; it += LU_T) {
+                // consecutive threads take consecutive ROWS of one chunk (conflict-free 16-byte accesses)
+                const int ch = it / nloc, i = it - ch * nloc;
+                const int base = ch * CH;
+                if (base + CH <= c + 1 || base >= w) continue;          // chunk entirely left of the pivot column
+                if (done[i] != w || lrow[i] == prow) continue;
+                double *__restrict__ t = tile + (size_t)i * TS;
+                const double nl = -(t[c] * rcp);
+                double2 tv[CH / 2], pvv[CH / 2];
+#pragma unroll
+                for (int k = 0; k < CH / 2; ++k) {      // all loads first: independent, pipelined
+                    tv[k] = *reinterpret_cast<const double2 *>(t + base + 2 * k);
+                    pvv[k] = *reinterpret_cast<const double2 *>(pvals + base + 2 * k);
                 }
-                if (lane == 0) { win_val = v; win_row = r; }
-            }
-            __syncthreads();
-            // ---- publish this CTA's candidate row (and the diagonal row) to every CTA ----------------------
-            const int wrow = win_row;
-            if (wrow == INT_MAX) {
-                if (tid == 0)
-                    for (int r = 0; r < LU_CL; ++r) {
-                        lu_cand *dst = cluster.map_shared_rank(&cand[buf][rank], r);
-                        dst->val = -1.0;
-                        dst->row = INT_MAX;
-                    }
-            }
 #pragma unroll
-            for (int q = 0; q < R; ++q) {
-                const int row = j0 + slot + q * nslots;
-                if (row == wrow) {
-                    for (int r = 0; r < LU_CL; ++r) {
-                        lu_cand *dst = cluster.map_shared_rank(&cand[buf][rank], r);
-                        dst->val = win_val;
-                        dst->row = row;
-#pragma unroll
-                        for (int k = 0; k < LU_W; ++k) dst->vals[k] = a[q][k];
-                    }
-                }
-                if (row == drow) {
-                    for (int r = 0; r < LU_CL; ++r) {
-                        double *dst = cluster.map_shared_rank(&diag[buf][0], r);
-#pragma unroll
-                        for (int k = 0; k < LU_W; ++k) dst[k] = a[q][k];
-                    }
-                }
-            }
-            cluster.sync();
-            // ---- every thread picks the global winner ------------------------------------------------------
-            double pv = -1.0;
-            int prow = INT_MAX, pr = 0;
-#pragma unroll
-            for (int r = 0; r < LU_CL; ++r) {
-                const double v = cand[buf][r].val;
-                const int row = cand[buf][r].row;
-                if (v > pv || (v == pv && row < prow)) { pv = v; prow = row; pr = r; }
-            }
-            double pvals[LU_W], dvals[LU_W];
-#pragma unroll
-            for (int k = 0; k < LU_W; ++k) { pvals[k] = cand[buf][pr].vals[k]; dvals[k] = diag[buf][k]; }
-            const bool singular = !(pv > 0.0);  // exactly zero (or NaN) column: LAPACK records info and moves on
-            if (singular) prow = drow;
-            if (slot == 0) {
-                piv[drow] = prow;
-                if (singular && *info == 0) *info = drow + 1;
-            }
-            if (!singular) {
-                if (prow != drow) {
-#pragma unroll
-                    for (int q = 0; q < R; ++q) {
-                        const int row = j0 + slot + q * nslots;
-                        if (row == prow) {
-#pragma unroll
-                            for (int k = 0; k < LU_W; ++k) a[q][k] = dvals[k];
-                        } else if (row == drow) {
-#pragma unroll
-                            for (int k = 0; k < LU_W; ++k) a[q][k] = pvals[k];
-                        }
-                    }
-                }
-                const double rcp = 1.0 / pvals[c];  // dgetf2 scales by the reciprocal
-#pragma unroll
-                for (int q = 0; q < R; ++q) {
-                    const int row = j0 + slot + q * nslots;
-                    if (row > drow && row < N) {
-                        const double l = a[q][c] * rcp;
-                        a[q][c] = l;
-#pragma unroll
-                        for (int c2 = c + 1; c2 < LU_W; ++c2) a[q][c2] = fma(-l, pvals[c2], a[q][c2]);
-                    }
+                for (int k = 0; k < CH / 2; ++k) {
+                    const int c2 = base + 2 * k;
+                    double2 o = tv[k];
+                    if (c2 > c && c2 < w) o.x = fma(nl, pvv[k].x, o.x);
+                    if (c2 + 1 > c && c2 + 1 < w) o.y = fma(nl, pvv[k].y, o.y);
+                    *reinterpret_cast<double2 *>(t + base + 2 * k) = o;
                 }
             }
         }
+        __syncthreads();   // eliminated values and the slot states are read by other threads in the next column
+        LU_STAMP(4);
     }
-#pragma unroll
-    for (int q = 0; q < R; ++q) {
-        const int row = j0 + slot + q * nslots;
-#pragma unroll
-        for (int c = 0; c < LU_W; ++c)
-            if (row < N && c < w) A[(int64_t)(j0 + c) * lda + row] = a[q][c];
+#ifdef SDB_LU_PROFILE
+    if (rank == 0 && tid == 0)
+        for (int k = 0; k < 5; ++k) g_lu_prof[k] += t_acc[k];
+#endif
+    // last interchange, then write back to the LOGICAL rows, scaling the sub-diagonal (L) entries
+    for (int i = tid; i < nloc; i += LU_T) {
+        if (done[i] == w && pcol >= 0) {
+            const int lr = lrow[i];
+            if (lr == prow) { lrow[i] = drow; done[i] = pcol; }
+            else if (lr == drow) lrow[i] = prow;
+        }
     }
+    __syncthreads();
+    if (rank == 0) {
+        for (int c = tid; c < w; c += LU_T) piv[j0 + c] = piv_s[c];
+        if (tid == 0 && sing_s != 0 && *info == 0) *info = sing_s;
+    }
+    for (int c = 0; c < w; ++c)
+        for (int i = tid; i < nloc; i += LU_T) {
+            double v = tile[i * TS + c];
+            if (c < done[i]) v *= rcp_s[c];
+            A[(int64_t)(j0 + c) * lda + lrow[i]] = v;
+        }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Row interchanges k = k0..k1-1 (row k <-> piv[k], in order) applied to columns [c0, c1).
+// Row interchanges k = k0..k1-1 (row k <-> piv[k], in order; k1 - k0 <= 64) applied to columns [c0, c1).
+// The sequence of swaps is first folded into its net permutation on the <= 2 (k1-k0) rows it touches
+// (one warp, shared memory); every thread then moves one column: all loads are independent (no chain of
+// dependent swaps), staged through shared memory, then stored.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) lu_laswp_kernel(double *__restrict__ A, int64_t lda, int c0, int c1,
-                                                       const int *__restrict__ piv, int k0, int k1) {
-    const int col = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+#define LASWP_T 64
+__global__ void __launch_bounds__(LASWP_T) lu_laswp_kernel(double *__restrict__ A, int64_t lda, int c0, int c1,
+                                                          const int *__restrict__ piv, int k0, int k1) {
+    extern __shared__ double stage[];      // [nS][LASWP_T]
+    __shared__ int rows[128], cont[128];   // destination row, source row
+    __shared__ int nS_s;
+    const int w = k1 - k0, lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) {
+        for (int i = lane; i < w; i += 32) { rows[i] = k0 + i; cont[i] = k0 + i; }
+        const int piv_lo = lane < w ? piv[k0 + lane] : 0, piv_hi = lane + 32 < w ? piv[k0 + 32 + lane] : 0;  // one coalesced load
+        __syncwarp();
+        int nS = w;
+        for (int k = 0; k < w; ++k) {
+            const int p = __shfl_sync(0xffffffffu, k < 32 ? piv_lo : piv_hi, k & 31);
+            if (p == k0 + k) continue;
+            int idx;
+            if (p < k1) idx = p - k0;
+            else {
+                unsigned hit = 0;
+                int found = -1;
+                for (int base = w; base < nS; base += 32) {
+                    const int e = base + lane;
+                    hit = __ballot_sync(0xffffffffu, e < nS && rows[e] == p);
+                    if (hit) { found = base + __ffs(hit) - 1; break; }
+                }
+                if (found < 0) {
+                    found = nS++;
+                    if (lane == 0) { rows[found] = p; cont[found] = p; }
+                }
+                idx = found;
+            }
+            __syncwarp();
+            if (lane == 0) { const int t = cont[k]; cont[k] = cont[idx]; cont[idx] = t; }
+            __syncwarp();
+        }
+        if (lane == 0) nS_s = nS;
+    }
+    __syncthreads();
+    const int nS = nS_s;
+    const int col = c0 + blockIdx.x * LASWP_T + threadIdx.x;
     if (col >= c1) return;
     double *a = A + (int64_t)col * lda;
-    for (int k = k0; k < k1; ++k) {
-        const int p = piv[k];
-        if (p != k) {
-            const double t = a[k];
-            a[k] = a[p];
-            a[p] = t;
+    for (int i0 = 0; i0 < nS; i0 += 16) {     // 16 independent loads in flight per thread
+        double v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int i = i0 + k;
+            v[k] = (i < nS && cont[i] != rows[i]) ? a[cont[i]] : 0.0;
         }
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (i0 + k < nS) stage[(i0 + k) * LASWP_T + threadIdx.x] = v[k];
     }
+    for (int i = 0; i < nS; ++i)
+        if (cont[i] != rows[i]) a[rows[i]] = stage[i * LASWP_T + threadIdx.x];
+}
+
+static int lu_laswp(cudaStream_t st, double *A, int64_t lda, int c0, int c1, const int *piv, int k0, int k1) {
+    if (c1 <= c0 || k1 <= k0) return SDB_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SDB_CUDA(cudaFuncSetAttribute((const void *)lu_laswp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      128 * LASWP_T * 8));
+        attr_set = true;
+    }
+    sdb_count_launch();
+    lu_laswp_kernel<<<(c1 - c0 + LASWP_T - 1) / LASWP_T, LASWP_T, 2 * (k1 - k0) * LASWP_T * 8, st>>>(A, lda, c0, c1, piv, k0, k1);
+    SDB_CUDA(cudaGetLastError());
+    return SDB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -227,6 +325,37 @@ __global__ void __launch_bounds__(128) lu_trsm_lunit_kernel(const double *__rest
         if (i < h) bp[i] = b[i];
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Panel-internal rank-h update with h, ncols <= 32:  C[M x ncols] -= L[M x h] * U[h x ncols]
+// (column-major, common leading dimension lda).  64 rows x 4 column groups per CTA; U in shared memory;
+// each thread keeps its row of L in registers.  Replaces a GEMM launch whose 128 x 64 tiles would be
+// mostly empty for these shapes.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lu_skinny_update_kernel(const double *__restrict__ Lp, const double *__restrict__ Up,
+                                                               double *__restrict__ Cp, int64_t lda, int M, int h, int ncols) {
+    __shared__ double Us[32][33];
+    for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+        const int k = e & 31, c = e >> 5;
+        Us[k][c] = (k < h && c < ncols) ? Up[(int64_t)c * lda + k] : 0.0;
+    }
+    __syncthreads();
+    const int r = blockIdx.x * 64 + (threadIdx.x & 63), cg = threadIdx.x >> 6;  // columns cg*8 .. cg*8+7
+    if (r >= M || cg * 8 >= ncols) return;
+    double l[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) l[k] = k < h ? Lp[(int64_t)k * lda + r] : 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = cg * 8 + j;
+        if (c < ncols) {
+            double acc = Cp[(int64_t)c * lda + r];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc = fma(-l[k], Us[k][c], acc);
+            Cp[(int64_t)c * lda + r] = acc;
+        }
+    }
+}
+
 static int lu_trsm_lunit(cudaStream_t st, const double *Lp, int64_t ldl, double *B, int64_t ldb, int h, int ncols) {
     if (ncols <= 0 || h <= 0) return SDB_OK;
     const int blocks = (ncols + 127) / 128;
@@ -238,45 +367,106 @@ static int lu_trsm_lunit(cudaStream_t st, const double *Lp, int64_t ldl, double 
     return SDB_OK;
 }
 
+// Cluster size and widest base case the shared memory allows for `rows` rows.
+struct lu_base_plan { int W, CL, rpc; size_t smem; };
+
+static int lu_cluster_size() {
+    // 16-CTA clusters are the non-portable maximum on sm_100; SDB_LU_CLUSTER overrides (8 is always legal)
+    static int v = 0;
+    if (!v) {
+        const char *e = getenv("SDB_LU_CLUSTER");
+        v = e ? atoi(e) : 16;
+        if (v != 16 && v != 8 && v != 4 && v != 2 && v != 1) v = 8;
+    }
+    return v;
+}
+
+static lu_base_plan lu_plan_base(int rows) {
+    const size_t budget = 180 * 1024;
+    lu_base_plan p;
+    p.CL = lu_cluster_size();
+    p.rpc = (rows + p.CL - 1) / p.CL;
+    const int widths[4] = {64, 32, 16, 8};
+    for (int k = 0; k < 4; ++k) {
+        p.W = widths[k];
+        p.smem = (size_t)p.rpc * (p.W + 2) * sizeof(double) + (size_t)p.rpc * 2 * sizeof(int) + 16;
+        if (p.smem <= budget) return p;
+    }
+    p.W = 0;
+    return p;
+}
+
+template <int W>
+static int lu_launch_base(cudaStream_t st, const lu_base_plan &p, double *A, int64_t lda, int N, int j0, int w, int *piv,
+                          int *info) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SDB_CUDA(cudaFuncSetAttribute((const void *)lu_base_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SDB_CUDA(cudaFuncSetAttribute((const void *)lu_base_kernel<W>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.CL, 1, 1);
+    cfg.blockDim = dim3(LU_T, 1, 1);
+    cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = p.CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    sdb_count_launch();
+    SDB_CUDA(cudaLaunchKernelEx(&cfg, lu_base_kernel<W>, A, lda, N, j0, w, p.rpc, piv, info));
+    return SDB_OK;
+}
+
+static int lu_base_width(int rows) { return lu_plan_base(rows).W; }
+
 static int lu_base(cudaStream_t st, double *A, int64_t lda, int N, int j0, int w, int *piv, int *info) {
-    const int rows = N - j0;
-    const int per = (rows + LU_CL * LU_T - 1) / (LU_CL * LU_T);
-    if (per <= 1) { sdb_count_launch(); lu_base_kernel<1><<<LU_CL, LU_T, 0, st>>>(A, lda, N, j0, w, piv, info); }
-    else if (per <= 2) { sdb_count_launch(); lu_base_kernel<2><<<LU_CL, LU_T, 0, st>>>(A, lda, N, j0, w, piv, info); }
-    else if (per <= 4) { sdb_count_launch(); lu_base_kernel<4><<<LU_CL, LU_T, 0, st>>>(A, lda, N, j0, w, piv, info); }
-    else if (per <= 8) { sdb_count_launch(); lu_base_kernel<8><<<LU_CL, LU_T, 0, st>>>(A, lda, N, j0, w, piv, info); }
-    else if (per <= 12) { sdb_count_launch(); lu_base_kernel<12><<<LU_CL, LU_T, 0, st>>>(A, lda, N, j0, w, piv, info); }
-    else {
-        sdb_set_error("sdb_lu: %d rows exceed the compiled limit of %d", rows, 12 * LU_CL * LU_T);
+    const lu_base_plan p = lu_plan_base(N - j0);
+    if (p.W == 0) {
+        sdb_set_error("sdb_lu: %d rows exceed the shared memory of one cluster", N - j0);
         return SDB_ERR_LIMIT;
     }
-    SDB_CUDA(cudaGetLastError());
-    return SDB_OK;
+    switch (p.W) {
+        case 64: return lu_launch_base<64>(st, p, A, lda, N, j0, w, piv, info);
+        case 32: return lu_launch_base<32>(st, p, A, lda, N, j0, w, piv, info);
+        case 16: return lu_launch_base<16>(st, p, A, lda, N, j0, w, piv, info);
+        default: return lu_launch_base<8>(st, p, A, lda, N, j0, w, piv, info);
+    }
 }
 
 // Recursive panel: columns [j0, j0 + w), rows [j0, N); interchanges applied inside the panel only.
 static int lu_panel(cudaStream_t st, double *A, int64_t lda, int N, int j0, int w, int *piv, int *info) {
-    if (w <= LU_W) return lu_base(st, A, lda, N, j0, w, piv, info);
-    const int h = ((w / 2 + LU_W - 1) / LU_W) * LU_W;  // left half, a multiple of the base width
+    const int bw = lu_base_width(N - j0);
+    if (w <= bw) return lu_base(st, A, lda, N, j0, w, piv, info);
+    const int h = ((w / 2 + bw - 1) / bw) * bw;  // left half, a multiple of the base width
     int rc = lu_panel(st, A, lda, N, j0, h, piv, info);
     if (rc) return rc;
     const int rcols = w - h;
-    sdb_count_launch();
-    lu_laswp_kernel<<<(rcols + 127) / 128, 128, 0, st>>>(A, lda, j0 + h, j0 + w, piv, j0, j0 + h);
+    rc = lu_laswp(st, A, lda, j0 + h, j0 + w, piv, j0, j0 + h);
+    if (rc) return rc;
     double *A11 = A + (int64_t)j0 * lda + j0;
     double *A12 = A + (int64_t)(j0 + h) * lda + j0;
     double *A21 = A11 + h;
     double *A22 = A12 + h;
     rc = lu_trsm_lunit(st, A11, lda, A12, lda, h, rcols);
     if (rc) return rc;
-    rc = sdb_gemm(st, N - j0 - h, rcols, h, -1.0, A21, 1, lda, A12, 1, lda, 1.0, A22, lda);
-    if (rc) return rc;
+    if (h <= 32 && rcols <= 32) {
+        const int M = N - j0 - h;
+        if (M > 0) {
+            sdb_count_launch();
+            lu_skinny_update_kernel<<<(M + 63) / 64, 256, 0, st>>>(A21, A12, A22, lda, M, h, rcols);
+        }
+    } else {
+        rc = sdb_gemm(st, N - j0 - h, rcols, h, -1.0, A21, 1, lda, A12, 1, lda, 1.0, A22, lda);
+        if (rc) return rc;
+    }
     rc = lu_panel(st, A, lda, N, j0 + h, rcols, piv, info);
     if (rc) return rc;
-    sdb_count_launch();
-    lu_laswp_kernel<<<(h + 127) / 128, 128, 0, st>>>(A, lda, j0, j0 + h, piv, j0 + h, j0 + w);
-    SDB_CUDA(cudaGetLastError());
-    return SDB_OK;
+    return lu_laswp(st, A, lda, j0, j0 + h, piv, j0 + h, j0 + w);
 }
 
 static int lu_factor(cudaStream_t st, double *A, int64_t lda, int N, int *piv, int *info) {
@@ -284,16 +474,17 @@ static int lu_factor(cudaStream_t st, double *A, int64_t lda, int N, int *piv, i
         const int w = (N - j0) < LU_NB ? (N - j0) : LU_NB;
         int rc = lu_panel(st, A, lda, N, j0, w, piv, info);
         if (rc) return rc;
-        if (j0 > 0) { sdb_count_launch(); lu_laswp_kernel<<<(j0 + 127) / 128, 128, 0, st>>>(A, lda, 0, j0, piv, j0, j0 + w); }
+        rc = lu_laswp(st, A, lda, 0, j0, piv, j0, j0 + w);
+        if (rc) return rc;
         const int rest = N - j0 - w;
         if (rest > 0) {
-            sdb_count_launch();
-            lu_laswp_kernel<<<(rest + 127) / 128, 128, 0, st>>>(A, lda, j0 + w, N, piv, j0, j0 + w);
+            rc = lu_laswp(st, A, lda, j0 + w, N, piv, j0, j0 + w);
+            if (rc) return rc;
             double *A11 = A + (int64_t)j0 * lda + j0;
             double *A12 = A + (int64_t)(j0 + w) * lda + j0;
             rc = lu_trsm_lunit(st, A11, lda, A12, lda, w, rest);
             if (rc) return rc;
-            rc = sdb_gemm(st, rest, rest, w, -1.0, A11 + w, 1, lda, A12, 1, lda, 1.0, A12 + w, lda);
+            rc = sdb_gemm_k64_update(st, rest, rest, w, A11 + w, A12, A12 + w, lda);
             if (rc) return rc;
         }
     }
@@ -379,6 +570,41 @@ static int lu_solve_factored(cudaStream_t st, const double *A, int64_t lda, int 
     return SDB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The factorisation is a chain of a few thousand short, dependent kernels whose sequence depends only on
+// (N, nrhs) and whose arguments depend only on the buffer addresses; issuing them one by one is bound by
+// the host's launch rate (~12 us per launch measured), not by the GPU.  So the whole sequence is captured
+// once per (buffers, N, nrhs) into a CUDA graph and replayed afterwards.  SDB_LU_GRAPH=0 disables this.
+// ---------------------------------------------------------------------------------------------------
+struct lu_graph_entry {
+    const void *A, *B, *piv, *info;
+    int64_t N;
+    int nrhs, device;
+    cudaGraphExec_t exec;
+    unsigned long long last_use;
+};
+#define LU_GRAPH_SLOTS 8
+static lu_graph_entry g_lu_graphs[LU_GRAPH_SLOTS];
+static unsigned long long g_lu_tick = 0;
+static long long g_lu_graph_nodes = 0;
+
+static int lu_enqueue(cudaStream_t st, double *d_A, int64_t N, double *d_B, int nrhs, int32_t *d_piv, int32_t *d_info) {
+    SDB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
+    int rc = lu_factor(st, d_A, N, (int)N, d_piv, d_info);
+    if (rc) return rc;
+    if (nrhs > 0) rc = lu_solve_factored(st, d_A, N, (int)N, d_piv, d_B, N, nrhs);
+    return rc;
+}
+
+static bool lu_graphs_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SDB_LU_GRAPH");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 // Factor A (column-major N x N, overwritten by L and U) and solve A X = B for nrhs columns
 // (B column-major N x nrhs, leading dimension N, overwritten by X).  d_piv: N ints.  d_info: 0, or
 // k+1 when U(k,k) is exactly zero (LAPACK's info).
@@ -388,11 +614,60 @@ extern "C" int sdb_lu_solve(double *d_A, int64_t N, double *d_B, int32_t nrhs, i
     SDB_CHECK_ARG(N >= 1 && N < (1 << 30), "sdb_lu_solve: N = %lld out of range", (long long)N);
     SDB_CHECK_ARG(nrhs >= 0 && (nrhs == 0 || d_B), "sdb_lu_solve: bad right-hand sides");
     cudaStream_t st = (cudaStream_t)stream;
-    SDB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
-    int rc = lu_factor(st, d_A, N, (int)N, d_piv, d_info);
-    if (rc) return rc;
-    if (nrhs > 0) rc = lu_solve_factored(st, d_A, N, (int)N, d_piv, d_B, N, nrhs);
-    return rc;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (st != nullptr) cudaStreamIsCapturing(st, &cs);
+    // small systems are not launch-bound enough to pay for an instantiation; the legacy default stream
+    // cannot be captured; a stream that is already being captured just records the kernels
+    if (!lu_graphs_enabled() || st == nullptr || cs != cudaStreamCaptureStatusNone || N < 256)
+        return lu_enqueue(st, d_A, N, d_B, nrhs, d_piv, d_info);
+    int dev = 0;
+    SDB_CUDA(cudaGetDevice(&dev));
+    lu_graph_entry *hit = nullptr, *victim = nullptr;
+    for (int i = 0; i < LU_GRAPH_SLOTS; ++i) {
+        lu_graph_entry &e = g_lu_graphs[i];
+        if (e.exec && e.A == d_A && e.B == d_B && e.piv == d_piv && e.info == d_info && e.N == N && e.nrhs == nrhs &&
+            e.device == dev) {
+            hit = &e;
+            break;
+        }
+    }
+    if (!hit) {
+        for (int i = 0; i < LU_GRAPH_SLOTS && !victim; ++i)
+            if (!g_lu_graphs[i].exec) victim = &g_lu_graphs[i];
+        if (!victim) {   // least recently used
+            victim = &g_lu_graphs[0];
+            for (int i = 1; i < LU_GRAPH_SLOTS; ++i)
+                if (g_lu_graphs[i].last_use < victim->last_use) victim = &g_lu_graphs[i];
+        }
+        // warm the lazily loaded kernels / attributes once outside the capture (first call in this process)
+        static bool warmed = false;
+        if (!warmed) {
+            warmed = true;
+            return lu_enqueue(st, d_A, N, d_B, nrhs, d_piv, d_info);
+        }
+        const long long before = sdb_launch_count(0);
+        cudaGraph_t graph = nullptr;
+        SDB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = lu_enqueue(st, d_A, N, d_B, nrhs, d_piv, d_info);
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) { sdb_set_error("sdb_lu_solve: graph capture failed: %s", cudaGetErrorString(ce)); return SDB_ERR_CUDA; }
+        if (victim->exec) cudaGraphExecDestroy(victim->exec);
+        victim->exec = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { sdb_set_error("sdb_lu_solve: graph instantiation failed: %s", cudaGetErrorString(ce)); return SDB_ERR_CUDA; }
+        g_lu_graph_nodes = sdb_launch_count(0) - before;
+        *victim = lu_graph_entry{d_A, d_B, d_piv, d_info, N, nrhs, dev, exec, 0};
+        hit = victim;
+    } else {
+        // replayed kernels are still launches of this library
+        for (long long k = 0; k < g_lu_graph_nodes; ++k) sdb_count_launch();
+    }
+    hit->last_use = ++g_lu_tick;
+    SDB_CUDA(cudaGraphLaunch(hit->exec, st));
+    return SDB_OK;
 }
 
 // C (column-major, ldc) = beta C + alpha A B with generic strides (see sdb_gemm.cuh); nslab > 1 splits K
@@ -404,3 +679,12 @@ extern "C" int sdb_dgemm(int32_t M, int32_t N, int32_t K, double alpha, const do
     SDB_CHECK_ARG(nslab <= 1 || d_ws, "sdb_dgemm: split-K needs a workspace");
     return sdb_gemm((cudaStream_t)stream, M, N, K, alpha, d_A, sa_m, sa_k, d_B, sb_k, sb_n, beta, d_C, ldc, nslab, d_ws);
 }
+
+#ifdef SDB_LU_PROFILE
+extern "C" SDB_API int sdb_lu_profile(long long *out8, int reset) {
+    long long z[8] = {0};
+    if (out8) cudaMemcpyFromSymbol(out8, g_lu_prof, sizeof(z));
+    if (reset) cudaMemcpyToSymbol(g_lu_prof, z, sizeof(z));
+    return 0;
+}
+#endif

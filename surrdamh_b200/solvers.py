@@ -33,7 +33,7 @@ class Solver_linela2exp_local:
         return np.float64(-f / (2 * self.k2) * (L * L) + uL_slope * L + offset)
 
     def device_model(self):
-        from .device import DeviceModel
+        from surrdamh_b200.device import DeviceModel
         return DeviceModel.toy(self.f, self.L, self.M)
 
 
@@ -50,7 +50,7 @@ class Solver_uninformative:
         return np.zeros((self.no_observations,))
 
     def device_model(self):
-        from .device import DeviceModel
+        from surrdamh_b200.device import DeviceModel
         return DeviceModel.zero(self.no_parameters, self.no_observations)
 
 
@@ -71,7 +71,7 @@ class Solver_frozen_surrogate:
         self._apply = None
 
     def device_model(self):
-        from .device import DeviceModel
+        from surrdamh_b200.device import DeviceModel
         if self._model is None:
             if self.kind == "rbf":
                 self._model = DeviceModel.rbf(self.SOL[0], self.SOL[1], self.kernel_type)
@@ -85,7 +85,7 @@ class Solver_frozen_surrogate:
     def get_observations(self):
         # host interface kept for completeness; evaluates on the GPU through the surrogate classes
         if self._apply is None:
-            from . import surrogate_poly, surrogate_rbf
+            from surrdamh_b200 import surrogate_poly, surrogate_rbf
             self._apply = (surrogate_rbf.Surrogate_apply(self.no_parameters, self.no_observations, self.kernel_type)
                            if self.kind == "rbf" else surrogate_poly.Surrogate_apply(self.no_parameters, self.no_observations))
         return self._apply.apply(self.device_model(), self.data_par)[0, :]

@@ -71,6 +71,8 @@ class Surrogate_update:
         self._obs = torch.empty((0, no_observations), dtype=torch.float64, device="cuda")
         self._new_par, self._new_obs = [], []
         self.last_info = None
+        self._work = None                   # persistent scratch: stable addresses let the LU graph be replayed
+        self._info_buf = torch.zeros((4,), dtype=torch.int32, device="cuda")
 
     @property
     def processed_par(self):
@@ -115,11 +117,14 @@ class Surrogate_update:
         n = self.no_processed = self._par.shape[0]
         N = n + d + 1
         COEFS = torch.empty((N, m), dtype=torch.float64, device="cuda")
-        info = torch.zeros((4,), dtype=torch.int32, device="cuda")
+        info = self._info_buf
+        info.zero_()
         if self.solver_type == "direct":
-            work = torch.empty((L.lib().sdb_rbf_fit_work(n, d, m),), dtype=torch.float64, device="cuda")
+            need = L.lib().sdb_rbf_fit_work(n, d, m)
+            if self._work is None or self._work.numel() < need:
+                self._work = torch.empty((need,), dtype=torch.float64, device="cuda")
             L.check(L.lib().sdb_rbf_fit(L.ptr(self._par), L.ptr(self._obs), n, d, m, int(self.kernel_type), L.ptr(COEFS),
-                                        L.ptr(work), L.ptr(info), L.stream_handle(stream)))
+                                        L.ptr(self._work), L.ptr(info), L.stream_handle(stream)))
         else:
             S = torch.empty((N, N), dtype=torch.float64, device="cuda")
             rhs = torch.empty((m, N), dtype=torch.float64, device="cuda")       # one contiguous column per observation
