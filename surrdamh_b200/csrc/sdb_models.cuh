@@ -113,7 +113,7 @@ __device__ __forceinline__ void sdb_rbf_partial_kt(const sdb_smodel &s, int d, i
     constexpr int MM = M ? M : SDB_MAX_M;
     constexpr int UM = M ? M : 1;
     const int n = s.n_centers;
-#pragma unroll 4
+#pragma unroll 8
     for (int i = first; i < n; i += stride) {
         const double *c = s.centers + (size_t)i * d;
         double r2 = 0.0;
