@@ -211,6 +211,14 @@ SDB_API int sdb_lu_solve(double *d_A, int64_t N, double *d_B, int32_t nrhs, int3
 SDB_API int64_t sdb_rbf_fit_work(int64_t n, int32_t d, int32_t m);
 SDB_API int sdb_rbf_fit(const double *d_X, const double *d_Y, int64_t n, int32_t d, int32_t m, int32_t kernel_type,
                         double *d_COEFS, double *d_work, int32_t *d_info, void *stream);
+/* The same system solved by the null-space method + Cholesky (no pivoting): Householder QR of P = [X, 1],
+ * B = Q^T phi(D) Q, Cholesky of the conditionally definite block.  Kernel types 0, 1, 4, 5, 6 only
+ * (SDB_ERR_ARG otherwise).  d_info: 0, or k+1 if the k-th Cholesky pivot was not positive (fall back to
+ * sdb_rbf_fit).  d_work: at least sdb_rbf_fit_nullspace_work(n, d, m).  An additive solver
+ * (Surrogate_update(solver_type='nullspace')); the reference has 'direct' and 'minres' only. */
+SDB_API int64_t sdb_rbf_fit_nullspace_work(int64_t n, int32_t d, int32_t m);
+SDB_API int sdb_rbf_fit_nullspace(const double *d_X, const double *d_Y, int64_t n, int32_t d, int32_t m, int32_t kernel_type,
+                                  double *d_COEFS, double *d_work, int32_t *d_info, void *stream);
 /* MINRES on a symmetric N x N matrix (scipy.sparse.linalg.minres as called at surrogate_rbf.py:131-135:
  * no shift, no preconditioner, stop on rtol).  d_x0 may be NULL.  d_work: at least 8*N + 64 doubles.
  * d_info: DEVICE int32[4] = {0 or maxiter (scipy's info), iterations, istop, 0}.  SYNCHRONISES the stream. */

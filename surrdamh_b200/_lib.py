@@ -83,6 +83,8 @@ _SIGNATURES = {
     "sdb_poly_fit": (C.c_int, [_P, _P, _L, _I, _I, C.POINTER(Model), _P, _P, _P, _P]),
     "sdb_rbf_fit_work": (C.c_int64, [_L, _I, _I]),
     "sdb_rbf_fit": (C.c_int, [_P, _P, _L, _I, _I, _I, _P, _P, _P, _P]),
+    "sdb_rbf_fit_nullspace_work": (C.c_int64, [_L, _I, _I]),
+    "sdb_rbf_fit_nullspace": (C.c_int, [_P, _P, _L, _I, _I, _I, _P, _P, _P, _P]),
     "sdb_rbf_system": (C.c_int, [_P, _P, _L, _I, _I, _I, _P, _P, _P]),
     "sdb_lu_solve": (C.c_int, [_P, _L, _P, _I, _P, _P, _P]),
     "sdb_rbf_thin_work": (C.c_int64, [_L]),

@@ -1,0 +1,378 @@
+// RBF interpolation system solved by the NULL-SPACE method + Cholesky (sm_100a, FP64).
+//
+// The saddle-point system  [[Phi, P], [P^T, 0]] [lambda; c] = [F; 0]  (surrogate_rbf.py:121-130) is
+// symmetric INDEFINITE, so the reference's 'direct' solver (and sdb_lu_solve) is an LU with partial pivoting
+// whose pivot search serialises the whole GPU once per column.  For the kernels that are conditionally
+// definite on the null space of P^T -- r (type 0, 6: negative definite there), r^3 (type 1), exp(-r^2)
+// (type 4) and (r^2+1)^(-1/2) (type 5) -- the same solution is obtained without any pivoting:
+//     P = Q [R; 0]                      Householder QR, q = d + 1 reflectors
+//     B = Q^T Phi Q,  g = Q^T F         two-sided reflector application, O(q n^2)
+//     y1 = 0,  (s B22) y2 = s g2        B22 = B[q:, q:] is s-definite (s = -1 for r, +1 otherwise): CHOLESKY
+//     R c = g1 - B12 y2,  lambda = Q [0; y2]
+// One third of the LU's flops, and the factorisation's critical path per 64 columns is a 64 x 64 POTRF in
+// one CTA instead of 64 cluster-wide pivot searches.  Opt-in (solver_type 'nullspace' of Surrogate_update);
+// a non-positive pivot is reported in info (the caller falls back to sdb_lu_solve).
+#include <float.h>
+
+#include "sdb_gemm.cuh"
+
+#define NS_T 1024
+
+__device__ __forceinline__ double ns_block_sum(double v, double *scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double t = lane < (blockDim.x >> 5) ? scratch[lane] : 0.0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Householder QR of P (n x q, column-major, leading dimension ldp), LAPACK dgeqr2 conventions: v_j below the
+// diagonal (v_j(j) = 1 implicit), R on and above it, tau[q].  Q^T is applied to the m columns of F (ldf).
+// One CTA: the norm of column j is a block reduction; the remaining columns are handled one per warp.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NS_T, 1) ns_house_qr_kernel(double *__restrict__ P, int64_t ldp, int n, int q,
+                                                              double *__restrict__ tau, double *__restrict__ F, int64_t ldf, int m) {
+    __shared__ double scratch[32];
+    __shared__ double s_tau, s_scale, s_beta;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    for (int j = 0; j < q && j < n; ++j) {
+        double *x = P + (int64_t)j * ldp;
+        double ss = 0.0;
+        for (int i = j + 1 + tid; i < n; i += blockDim.x) ss = fma(x[i], x[i], ss);
+        ss = ns_block_sum(ss, scratch);
+        if (tid == 0) {
+            const double alpha = x[j];
+            if (ss == 0.0) { s_tau = 0.0; s_scale = 0.0; s_beta = alpha; }
+            else {
+                const double beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+                s_tau = (beta - alpha) / beta;
+                s_scale = 1.0 / (alpha - beta);
+                s_beta = beta;
+            }
+        }
+        __syncthreads();
+        const double tj = s_tau, sc = s_scale;
+        for (int i = j + 1 + tid; i < n; i += blockDim.x) x[i] *= sc;
+        if (tid == 0) { x[j] = s_beta; tau[j] = tj; }
+        __syncthreads();
+        // apply H_j = I - tau v v^T to the later columns of P and to F: one warp per column
+        const int ncol = (q - 1 - j) + m;
+        for (int cc = warp; cc < ncol; cc += nwarp) {
+            double *col = cc < q - 1 - j ? P + (int64_t)(j + 1 + cc) * ldp : F + (int64_t)(cc - (q - 1 - j)) * ldf;
+            double w = 0.0;
+            for (int i = j + 1 + lane; i < n; i += 32) w = fma(x[i], col[i], w);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(0xffffffffu, w, off);
+            w += col[j];                      // v_j(j) = 1
+            const double tw = tj * w;
+            for (int i = j + 1 + lane; i < n; i += 32) col[i] = fma(-tw, x[i], col[i]);
+            if (lane == 0) col[j] -= tw;
+        }
+        __syncthreads();
+    }
+}
+
+// explicit reflector vector v_j (length n): 0 above j, 1 at j, P(i, j) below
+__global__ void __launch_bounds__(256) ns_vec_kernel(const double *__restrict__ P, int64_t ldp, int n, int j, double *__restrict__ v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i < j ? 0.0 : (i == j ? 1.0 : P[(int64_t)j * ldp + i]);
+}
+
+// w = Phi v, Phi symmetric n x n with leading dimension ld; one warp per row
+__global__ void __launch_bounds__(256) ns_symv_kernel(const double *__restrict__ Phi, int64_t ld, int n, const double *__restrict__ v,
+                                                      double *__restrict__ w) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const double *a = Phi + (int64_t)row * ld;
+    double s = 0.0;
+    for (int c = lane; c < n; c += 32) s = fma(a[c], v[c], s);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) w[row] = s;
+}
+
+// z = tau w - (tau^2 (v.w) / 2) v
+__global__ void __launch_bounds__(NS_T, 1) ns_z_kernel(int n, const double *__restrict__ v, const double *__restrict__ w,
+                                                       const double *__restrict__ tau, int j, double *__restrict__ z) {
+    __shared__ double scratch[32];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a = fma(v[i], w[i], a);
+    a = ns_block_sum(a, scratch);
+    const double t = tau[j], h = 0.5 * t * t * a;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) z[i] = t * w[i] - h * v[i];
+}
+
+// Phi -= v z^T + z v^T; entries with r >= q0 and c >= q0 are additionally multiplied by `scale` (the sign that
+// makes B22 positive definite, applied with the last reflector)
+__global__ void __launch_bounds__(256) ns_syr2_kernel(double *__restrict__ Phi, int64_t ld, int n, const double *__restrict__ v,
+                                                      const double *__restrict__ z, int q0, double scale) {
+    const int r = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int c0 = blockIdx.y * 32 + (threadIdx.x >> 5) * 4;
+    if (r >= n) return;
+    const double vr = v[r], zr = z[r];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + k;
+        if (c < n) {
+            double *p = Phi + (int64_t)c * ld + r;
+            double val = *p - (vr * z[c] + zr * v[c]);
+            if (r >= q0 && c >= q0) val *= scale;
+            *p = val;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Cholesky (lower, column-major, leading dimension ld) of the nb x nb matrix A, 64-column blocks
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) chol_potrf64_kernel(double *__restrict__ A, int64_t ld, int k0, int h, int *__restrict__ info) {
+    __shared__ double T[64][65];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 64 * 64; e += 256) {
+        const int i = e & 63, c = e >> 6;
+        T[i][c] = (i < h && c <= i) ? A[(int64_t)(k0 + c) * ld + k0 + i] : 0.0;
+    }
+    __syncthreads();
+    for (int j = 0; j < h; ++j) {
+        const double djj = T[j][j];
+        if (!(djj > 0.0)) {                       // not positive definite (or NaN): report, keep going harmlessly
+            if (tid == 0 && *info == 0) *info = k0 + j + 1;
+        }
+        const double d = djj > 0.0 ? sqrt(djj) : 1.0;
+        const double rd = 1.0 / d;
+        __syncthreads();
+        if (tid == 0) T[j][j] = d;
+        for (int i = j + 1 + tid; i < h; i += 256) T[i][j] *= rd;
+        __syncthreads();
+        // trailing update of the lower triangle: (i, c), j < c <= i < h
+        const int rem = h - j - 1;
+        for (int e = tid; e < rem * rem; e += 256) {
+            const int i = j + 1 + e % rem, c = j + 1 + e / rem;
+            if (c <= i) T[i][c] = fma(-T[i][j], T[c][j], T[i][c]);
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < 64 * 64; e += 256) {
+        const int i = e & 63, c = e >> 6;
+        if (i < h && c <= i) A[(int64_t)(k0 + c) * ld + k0 + i] = T[i][c];
+    }
+}
+
+// L21 := A21 L11^{-T}: one thread per row of A21 (rows k0+h .. nb-1), the row in registers, L11 in shared memory
+__global__ void __launch_bounds__(128) chol_trsm_kernel(double *__restrict__ A, int64_t ld, int k0, int h, int nb) {
+    __shared__ double T[64][65];
+    __shared__ double rdiag[64];
+    for (int e = threadIdx.x; e < 64 * 64; e += 128) {
+        const int i = e & 63, c = e >> 6;
+        T[i][c] = (i < h && c <= i) ? A[(int64_t)(k0 + c) * ld + k0 + i] : 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) rdiag[threadIdx.x] = threadIdx.x < h ? 1.0 / T[threadIdx.x][threadIdx.x] : 1.0;
+    __syncthreads();
+    const int r = k0 + h + blockIdx.x * 128 + threadIdx.x;
+    if (r >= nb) return;
+    double x[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) x[c] = c < h ? A[(int64_t)(k0 + c) * ld + r] : 0.0;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) {
+        double t = x[c];
+#pragma unroll
+        for (int k = 0; k < c; ++k) t = fma(-x[k], T[c][k], t);
+        x[c] = t * rdiag[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 64; ++c)
+        if (c < h) A[(int64_t)(k0 + c) * ld + r] = x[c];
+}
+
+// one warp per right-hand side: x = L11^{-1} b (TRANS = false) or L11^{-T} b (TRANS = true) on a block of h <= 64 rows
+template <bool TRANS>
+__global__ void __launch_bounds__(256) chol_trsv_block_kernel(const double *__restrict__ A, int64_t ld, double *__restrict__ B,
+                                                              int64_t ldb, int k0, int h, int nrhs) {
+    __shared__ double T[64][65];   // T[i][k] = L(k0+i, k0+k), k <= i
+    for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+        const int i = e & 63, k = e >> 6;
+        T[i][k] = (i < h && k <= i) ? A[(int64_t)(k0 + k) * ld + k0 + i] : (i == k ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int rhs = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rhs < nrhs; rhs += gridDim.x * (blockDim.x >> 5)) {
+        double *b = B + (int64_t)rhs * ldb + k0;
+        double x0 = lane < h ? b[lane] : 0.0, x1 = lane + 32 < h ? b[lane + 32] : 0.0;
+        if (!TRANS) {
+            for (int i = 0; i < h; ++i) {
+                double xi = __shfl_sync(0xffffffffu, i < 32 ? x0 : x1, i & 31);
+                xi = xi / T[i][i];
+                if (lane == (i & 31)) { if (i < 32) x0 = xi; else x1 = xi; }
+                if (lane > i) x0 = fma(-T[lane][i], xi, x0);
+                if (lane + 32 > i) x1 = fma(-T[lane + 32][i], xi, x1);
+            }
+        } else {
+            for (int i = h - 1; i >= 0; --i) {
+                double xi = __shfl_sync(0xffffffffu, i < 32 ? x0 : x1, i & 31);
+                xi = xi / T[i][i];
+                if (lane == (i & 31)) { if (i < 32) x0 = xi; else x1 = xi; }
+                if (lane < i) x0 = fma(-T[i][lane], xi, x0);            // L^T(lane, i) = L(i, lane)
+                if (lane + 32 < i) x1 = fma(-T[i][lane + 32], xi, x1);
+            }
+        }
+        if (lane < h) b[lane] = x0;
+        if (lane + 32 < h) b[lane + 32] = x1;
+    }
+}
+
+__global__ void __launch_bounds__(256) ns_scale_rhs_kernel(double *__restrict__ F, int64_t ldf, int q, int n, int m, double scale) {
+    const int64_t total = (int64_t)(n - q) * m;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(e / (n - q)), i = q + (int)(e % (n - q));
+        F[(int64_t)k * ldf + i] *= scale;
+    }
+}
+
+// c = R^{-1} (g1 - B12 y2),  lambda = Q [0; y2]  ->  COEFS [(n + q) x m] row-major.  One CTA per right-hand side.
+__global__ void __launch_bounds__(NS_T, 1) ns_finish_kernel(const double *__restrict__ S, int64_t ld, int n, int q,
+                                                            const double *__restrict__ tau, double *__restrict__ F, int64_t ldf,
+                                                            int m, double *__restrict__ COEFS) {
+    __shared__ double scratch[32];
+    __shared__ double t1[SDB_MAX_D + 1], cc[SDB_MAX_D + 1];
+    const int rhs = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    double *f = F + (int64_t)rhs * ldf;
+    const double *P = S + (int64_t)n * ld;          // columns n .. n+q-1: reflectors below, R on / above the diagonal
+    // t1_i = g1_i - sum_c B12(i, c) y2_c,  B12(i, c) = S[c*ld + i] (unscaled rows i < q)
+    for (int i = warp; i < q; i += nwarp) {
+        double s = 0.0;
+        for (int c = q + lane; c < n; c += 32) s = fma(S[(int64_t)c * ld + i], f[c], s);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) t1[i] = f[i] - s;
+    }
+    __syncthreads();
+    if (tid == 0) {                                   // R c = t1, R upper triangular
+        for (int i = q - 1; i >= 0; --i) {
+            double s = t1[i];
+            for (int k = i + 1; k < q; ++k) s -= P[(int64_t)k * ld + i] * cc[k];
+            cc[i] = s / P[(int64_t)i * ld + i];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < q; i += blockDim.x) f[i] = 0.0;      // [0; y2]
+    __syncthreads();
+    for (int j = q - 1; j >= 0; --j) {                          // lambda = H_0 ... H_{q-1} [0; y2]
+        const double *v = P + (int64_t)j * ld;
+        double w = 0.0;
+        for (int i = j + 1 + tid; i < n; i += blockDim.x) w = fma(v[i], f[i], w);
+        w = ns_block_sum(w, scratch);
+        w += f[j];
+        const double tw = tau[j] * w;
+        __syncthreads();
+        for (int i = j + 1 + tid; i < n; i += blockDim.x) f[i] = fma(-tw, v[i], f[i]);
+        if (tid == 0) f[j] -= tw;
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += blockDim.x) COEFS[(int64_t)i * m + rhs] = f[i];
+    for (int i = tid; i < q; i += blockDim.x) COEFS[(int64_t)(n + i) * m + rhs] = cc[i];
+}
+
+static bool ns_kernel_supported(int kt) { return kt == 0 || kt == 1 || kt == 4 || kt == 5 || kt == 6; }
+
+static int ns_enqueue(cudaStream_t st, double *S, int n, int d, int m, int kernel_type, double *F, double *COEFS,
+                      double *vec, int32_t *d_info) {
+    const int q = d + 1, N = n + q, nb = n - q;
+    const int64_t ld = N;
+    double *P = S + (int64_t)n * ld;
+    double *tau = vec, *v = vec + 64, *w = v + n, *z = w + n;
+    const double sgn = (kernel_type == 0 || kernel_type == 6) ? -1.0 : 1.0;
+    SDB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
+    sdb_count_launch();
+    ns_house_qr_kernel<<<1, NS_T, 0, st>>>(P, ld, n, q, tau, F, ld, m);
+    for (int j = 0; j < q; ++j) {
+        sdb_count_launch();
+        ns_vec_kernel<<<(n + 255) / 256, 256, 0, st>>>(P, ld, n, j, v);
+        sdb_count_launch();
+        ns_symv_kernel<<<(n + 7) / 8, 256, 0, st>>>(S, ld, n, v, w);
+        sdb_count_launch();
+        ns_z_kernel<<<1, NS_T, 0, st>>>(n, v, w, tau, j, z);
+        sdb_count_launch();
+        ns_syr2_kernel<<<dim3((n + 31) / 32, (n + 31) / 32), 256, 0, st>>>(S, ld, n, v, z, q, j == q - 1 ? sgn : 1.0);
+    }
+    if (sgn != 1.0) {
+        sdb_count_launch();
+        ns_scale_rhs_kernel<<<148, 256, 0, st>>>(F, ld, q, n, m, sgn);
+    }
+    // Cholesky of B22 = S[q:n, q:n]
+    double *A = S + (int64_t)q * ld + q;
+    for (int k0 = 0; k0 < nb; k0 += 64) {
+        const int h = (nb - k0) < 64 ? (nb - k0) : 64;
+        sdb_count_launch();
+        chol_potrf64_kernel<<<1, 256, 0, st>>>(A, ld, k0, h, d_info);
+        const int rest = nb - k0 - h;
+        if (rest > 0) {
+            sdb_count_launch();
+            chol_trsm_kernel<<<(rest + 127) / 128, 128, 0, st>>>(A, ld, k0, h, nb);
+            double *L21 = A + (int64_t)k0 * ld + k0 + h;
+            double *A22 = A + (int64_t)(k0 + h) * ld + k0 + h;
+            int rc = sdb_syrk_k64_update(st, rest, rest, h, L21, L21, A22, ld);
+            if (rc) return rc;
+        }
+    }
+    // (s B22) y2 = s g2: forward with L, backward with L^T, m right-hand sides living in F[q:n]
+    double *G2 = F + q;
+    const int tb = (m + 7) / 8;
+    for (int k0 = 0; k0 < nb; k0 += 64) {
+        const int h = (nb - k0) < 64 ? (nb - k0) : 64;
+        sdb_count_launch();
+        chol_trsv_block_kernel<false><<<tb, 256, 0, st>>>(A, ld, G2, ld, k0, h, m);
+        const int rest = nb - k0 - h;
+        if (rest > 0) {
+            int rc = sdb_gemm(st, rest, m, h, -1.0, A + (int64_t)k0 * ld + k0 + h, 1, ld, G2 + k0, 1, ld, 1.0, G2 + k0 + h, ld);
+            if (rc) return rc;
+        }
+    }
+    for (int k1 = nb; k1 > 0;) {
+        const int h = (k1 % 64) ? (k1 % 64) : 64;
+        const int k0 = k1 - h;
+        sdb_count_launch();
+        chol_trsv_block_kernel<true><<<tb, 256, 0, st>>>(A, ld, G2, ld, k0, h, m);
+        if (k0 > 0) {   // w[0:k0] -= L[k0:k0+h, 0:k0]^T y_block
+            int rc = sdb_gemm(st, k0, m, h, -1.0, A + k0, ld, 1, G2 + k0, 1, ld, 1.0, G2, ld);
+            if (rc) return rc;
+        }
+        k1 = k0;
+    }
+    sdb_count_launch();
+    ns_finish_kernel<<<m, NS_T, 0, st>>>(S, ld, n, q, tau, F, ld, m, COEFS);
+    SDB_CUDA(cudaGetLastError());
+    return SDB_OK;
+}
+
+extern "C" int64_t sdb_rbf_fit_nullspace_work(int64_t n, int32_t d, int32_t m) {
+    const int64_t N = n + d + 1;
+    return N * N + N * m + 3 * n + 128;   // system | right-hand sides | tau, v, w, z
+}
+
+// Same contract as sdb_rbf_fit (X [n x d], Y [n x m] -> d_COEFS [(n+d+1) x m] row-major) for kernel types
+// 0, 1, 4, 5, 6.  d_info: 0, or k+1 if the k-th pivot of the Cholesky factorisation was not positive (the
+// projected kernel matrix is numerically not definite: use sdb_rbf_fit).  SDB_ERR_ARG for other kernel types.
+extern "C" int sdb_rbf_fit_nullspace(const double *d_X, const double *d_Y, int64_t n, int32_t d, int32_t m, int32_t kernel_type,
+                                     double *d_COEFS, double *d_work, int32_t *d_info, void *stream) {
+    SDB_CHECK_ARG(d_X && d_Y && d_COEFS && d_work && d_info, "sdb_rbf_fit_nullspace: NULL pointer");
+    SDB_CHECK_ARG(ns_kernel_supported(kernel_type),
+                  "sdb_rbf_fit_nullspace: kernel_type %d is not conditionally definite with a linear tail (use sdb_rbf_fit)", kernel_type);
+    SDB_CHECK_ARG(n > d + 1, "sdb_rbf_fit_nullspace: needs more than d + 1 points");
+    SDB_CHECK_LIMIT(d >= 1 && d <= SDB_MAX_D && m >= 1 && m <= SDB_MAX_M, "sdb_rbf_fit_nullspace: d=%d m=%d outside limits", d, m);
+    const int64_t N = n + d + 1;
+    double *S = d_work;
+    double *F = S + N * N;
+    double *vec = F + N * m;
+    int rc = sdb_rbf_system(d_X, d_Y, n, d, m, kernel_type, S, F, stream);
+    if (rc) return rc;
+    return ns_enqueue((cudaStream_t)stream, S, (int)n, d, m, kernel_type, F, d_COEFS, vec, d_info);
+}

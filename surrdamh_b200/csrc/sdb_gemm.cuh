@@ -193,14 +193,21 @@ __device__ __forceinline__ void sdb_cp_async8(void *smem, const void *gmem, bool
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
 }
 
+// BT = false: B(k, j) = B[j*ld + k]  (k-contiguous: the U12 block of the LU);  shared layout Bs[n][k]
+// BT = true : B(k, j) = B[k*ld + j]  (j-contiguous: B = L21^T of the Cholesky SYRK); shared layout Bs[k][n]
+// LOWER: tiles strictly above the diagonal are skipped (symmetric rank-k update of the lower triangle)
+template <bool BT, bool LOWER>
 static __global__ void __launch_bounds__(256, 2) sdb_gemm_k64_kernel(const double *__restrict__ A, const double *__restrict__ B,
                                                                      double *__restrict__ C, int64_t ld, int M, int N, int K) {
+    const int m0 = blockIdx.x * GM_BM, n0 = blockIdx.y * GM_BN;
+    if (LOWER && n0 > m0 + GM_BM - 1) return;
     extern __shared__ __align__(16) double gk_sm[];
-    double (*As)[GM_BM + GK_APAD] = (double (*)[GM_BM + GK_APAD])gk_sm;                               // [64][136]
-    double (*Bs)[GK_K + GK_BPAD] = (double (*)[GK_K + GK_BPAD])(gk_sm + GK_K * (GM_BM + GK_APAD));     // [64 n][68]
+    double (*As)[GM_BM + GK_APAD] = (double (*)[GM_BM + GK_APAD])gk_sm;                               // [64 k][136]
+    double *Bsm = gk_sm + GK_K * (GM_BM + GK_APAD);
+    double (*Bs)[GK_K + GK_BPAD] = (double (*)[GK_K + GK_BPAD])Bsm;                                   // [64 n][68]   (!BT)
+    double (*Bt)[GM_BN + GK_APAD] = (double (*)[GM_BN + GK_APAD])Bsm;                                 // [64 k][72]   (BT)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
-    const int m0 = blockIdx.x * GM_BM, n0 = blockIdx.y * GM_BN;
     const int gid = lane >> 2, tig = lane & 3;
     // two halves of K: rows [0,32) and [32,64) of As / Bs
 #pragma unroll
@@ -214,13 +221,19 @@ static __global__ void __launch_bounds__(256, 2) sdb_gemm_k64_kernel(const doubl
             const bool ok = (m0 + mm < M) && (kk < K);
             sdb_cp_async8(&As[kk][mm], A + (int64_t)kk * ld + (m0 + mm), ok);
         }
-        // B: 32 k x 64 n (2048 elements, 8 per thread), k fastest over threads (contiguous in memory)
+        // B: 32 k x 64 n (2048 elements, 8 per thread), the memory-contiguous index fastest over threads
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int idx = tid + e * 256;
-            const int kk = kb + (idx & 31), nn = idx >> 5;
-            const bool ok = (n0 + nn < N) && (kk < K);
-            sdb_cp_async8(&Bs[nn][kk], B + (int64_t)(n0 + nn) * ld + kk, ok);
+            if (!BT) {
+                const int kk = kb + (idx & 31), nn = idx >> 5;
+                const bool ok = (n0 + nn < N) && (kk < K);
+                sdb_cp_async8(&Bs[nn][kk], B + (int64_t)(n0 + nn) * ld + kk, ok);
+            } else {
+                const int nn = idx & 63, kk = kb + (idx >> 6);
+                const bool ok = (n0 + nn < N) && (kk < K);
+                sdb_cp_async8(&Bt[kk][nn], B + (int64_t)kk * ld + (n0 + nn), ok);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -242,7 +255,7 @@ static __global__ void __launch_bounds__(256, 2) sdb_gemm_k64_kernel(const doubl
 #pragma unroll
                 for (int i = 0; i < 4; ++i) fa[i] = As[k + tig][wm + i * 8 + gid];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) fb[j] = Bs[wn + j * 8 + gid][k + tig];
+                for (int j = 0; j < 4; ++j) fb[j] = BT ? Bt[k + tig][wn + j * 8 + gid] : Bs[wn + j * 8 + gid][k + tig];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -264,18 +277,30 @@ static __global__ void __launch_bounds__(256, 2) sdb_gemm_k64_kernel(const doubl
             }
 }
 
-static inline int sdb_gemm_k64_update(cudaStream_t st, int M, int N, int K, const double *A, const double *B, double *C,
+template <bool BT, bool LOWER>
+static inline int sdb_gemm_k64_launch(cudaStream_t st, int M, int N, int K, const double *A, const double *B, double *C,
                                       int64_t ld) {
     if (M <= 0 || N <= 0 || K <= 0) return SDB_OK;
-    const int smem = (GK_K * (GM_BM + GK_APAD) + GM_BN * (GK_K + GK_BPAD)) * 8;
+    const int smem = (GK_K * (GM_BM + GK_APAD) + GK_K * (GM_BN + GK_APAD)) * 8;
     static bool attr_set = false;
     if (!attr_set) {
-        SDB_CUDA(cudaFuncSetAttribute((const void *)sdb_gemm_k64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SDB_CUDA(cudaFuncSetAttribute((const void *)sdb_gemm_k64_kernel<BT, LOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     dim3 grid((M + GM_BM - 1) / GM_BM, (N + GM_BN - 1) / GM_BN);
     sdb_count_launch();
-    sdb_gemm_k64_kernel<<<grid, 256, smem, st>>>(A, B, C, ld, M, N, K);
+    sdb_gemm_k64_kernel<BT, LOWER><<<grid, 256, smem, st>>>(A, B, C, ld, M, N, K);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
+}
+
+// C -= A B, B = U12 (k-contiguous): the LU trailing update
+static inline int sdb_gemm_k64_update(cudaStream_t st, int M, int N, int K, const double *A, const double *B, double *C,
+                                      int64_t ld) {
+    return sdb_gemm_k64_launch<false, false>(st, M, N, K, A, B, C, ld);
+}
+// lower(C) -= A A2^T with A2 given as rows (B(k, j) = A2[k*ld + j]): the Cholesky trailing update
+static inline int sdb_syrk_k64_update(cudaStream_t st, int M, int N, int K, const double *A, const double *A2, double *C,
+                                      int64_t ld) {
+    return sdb_gemm_k64_launch<true, true>(st, M, N, K, A, A2, C, ld);
 }

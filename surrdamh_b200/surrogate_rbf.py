@@ -119,7 +119,20 @@ class Surrogate_update:
         COEFS = torch.empty((N, m), dtype=torch.float64, device="cuda")
         info = self._info_buf
         info.zero_()
-        if self.solver_type == "direct":
+        done = False
+        if self.solver_type == "nullspace" and int(self.kernel_type) in (0, 1, 4, 5, 6) and n > d + 1:
+            # additive solver: null-space method + Cholesky (no pivoting); falls back to the pivoted LU below
+            # if the projected kernel matrix is numerically not definite
+            need = L.lib().sdb_rbf_fit_nullspace_work(n, d, m)
+            if self._work is None or self._work.numel() < need:
+                self._work = torch.empty((need,), dtype=torch.float64, device="cuda")
+            L.check(L.lib().sdb_rbf_fit_nullspace(L.ptr(self._par), L.ptr(self._obs), n, d, m, int(self.kernel_type),
+                                                  L.ptr(COEFS), L.ptr(self._work), L.ptr(info), L.stream_handle(stream)))
+            done = int(info[0].item()) == 0
+            self.fallbacks = getattr(self, "fallbacks", 0) + (0 if done else 1)
+        if done:
+            pass
+        elif self.solver_type in ("direct", "nullspace"):
             need = L.lib().sdb_rbf_fit_work(n, d, m)
             if self._work is None or self._work.numel() < need:
                 self._work = torch.empty((need,), dtype=torch.float64, device="cuda")
@@ -147,6 +160,6 @@ class Surrogate_update:
     def update(self):
         mo, n = self.update_device()
         self.last_info = self._info.cpu().numpy()
-        if self.solver_type == "direct" and self.last_info[0] != 0:
+        if self.solver_type in ("direct", "nullspace") and self.last_info[0] != 0:
             raise np.linalg.LinAlgError("Singular matrix")          # what np.linalg.solve raises
         return [mo.coefs.cpu().numpy(), mo.centers.cpu().numpy()], n

@@ -271,3 +271,44 @@ def test_poly_fit_large_well_conditioned(L):
         (Mr, dgr), _ = ref.update()
         assert dg == dgr == deg and cnt == n
         assert close(M, Mr, rtol=1e-10), (d, m)
+
+
+def test_rbf_nullspace_cholesky_matches_direct(L):
+    """Additive solver_type 'nullspace' (Householder null-space projection + Cholesky, no pivoting): the same
+    solution as the pivoted LU / LAPACK within cond * eps, for every kernel type it accepts, including the
+    golden two-batch + thinning cases; unsupported kernel types fall back to the LU."""
+    from surrdamh_b200 import surrogate_rbf as SR
+    rs = np.random.RandomState(8)
+    for d, m, n, kt in ((2, 1, 900, 1), (4, 3, 700, 1), (3, 2, 500, 0), (4, 3, 400, 4), (4, 3, 400, 5), (8, 2, 300, 6),
+                        (2, 1, 2100, 1), (32, 3, 600, 1)):
+        X = rs.standard_normal((n, d))
+        Y = np.stack([np.sin((k + 1) * X).sum(axis=1) for k in range(m)], axis=1)
+        up = SR.Surrogate_update(d, m, kernel_type=kt, solver_type="nullspace")
+        up.add_arrays(X, Y)
+        (CO, Cc), nn = up.update()
+        assert getattr(up, "fallbacks", 0) == 0, (d, m, n, kt)
+        ref = ORB.RbfUpdate(d, m, kernel_type=kt, solver_type="direct")
+        ref.add_arrays(X, Y)
+        (COr, _), _ = ref.update()
+        S, R = ref.last_system, ref.last_rhs
+        res = np.linalg.norm(S @ CO - R) / (np.linalg.norm(S) * np.linalg.norm(CO))
+        res_ref = np.linalg.norm(S @ COr - R) / (np.linalg.norm(S) * np.linalg.norm(COr))
+        assert res <= 20 * res_ref + 1e-16, (d, m, n, kt, res, res_ref)
+        cond = np.linalg.cond(S)
+        assert np.linalg.norm(CO - COr) <= 50 * cond * 2.2e-16 * np.linalg.norm(COr), (d, m, n, kt, cond)
+        # evaluation parity on the training set and on fresh points
+        ev = ORB.RbfApply(d, m, kernel_type=kt)
+        pts = np.vstack([X[:200], rs.standard_normal((100, d))])
+        assert close(ev.apply([CO, Cc], pts), ev.apply([COr, Cc], pts), rtol=1e-7), (d, m, n, kt)
+    g = load("rbf")
+    X, Y = g["update_X"], g["update_Y"]
+    for i, (kt, minres, keep) in enumerate(g["update_cases"]):
+        if minres:
+            continue
+        up = SR.Surrogate_update(4, 3, kernel_type=int(kt), solver_type="nullspace", no_keep=None if keep < 0 else int(keep))
+        up.add_data([Snap(X[j], Y[j]) for j in range(70)])
+        up.update()
+        up.add_data([Snap(X[j], Y[j]) for j in range(70, 160)])
+        (CO2, C2), n2 = up.update()
+        assert n2 == g[f"update{i}_n"][1] and np.array_equal(C2, g[f"update{i}_centers2"])
+        assert close(CO2, g[f"update{i}_coefs2"], rtol=1e-5), (i, kt)       # kt 2, 3, 7 take the LU path

@@ -50,9 +50,15 @@ def main():
         keep = torch.empty((n + 256,), dtype=torch.uint8, device="cuda")
         wk = torch.empty((h.sdb_rbf_thin_work(n + 256),), dtype=torch.float64, device="cuda")
         t_thin = ev_time(lambda: L.check(h.sdb_rbf_thin(L.ptr(Xt), n + 256, d, n, L.ptr(keep), L.ptr(wk), L.stream_handle())))
+        # null-space + Cholesky
+        CO = torch.empty((N, m), dtype=torch.float64, device="cuda")
+        wk2 = torch.empty((h.sdb_rbf_fit_nullspace_work(n, d, m),), dtype=torch.float64, device="cuda")
+        t_ns = ev_time(lambda: L.check(h.sdb_rbf_fit_nullspace(L.ptr(X), L.ptr(Y), n, d, m, 1, L.ptr(CO), L.ptr(wk2), L.ptr(info), L.stream_handle())))
+        xns = CO.cpu().numpy()
+        res_ns = np.linalg.norm(Sn @ xns - Rn) / (np.linalg.norm(Sn) * np.linalg.norm(xns))
         flops = 2.0 / 3.0 * N ** 3
-        print("n=%6d  system %.3f ms  lu+solve %.3f ms (%.2f TF/s, %d launches, backward error %.1e)  thin(+256) %.3f ms"
-              % (n, t_sys[0], t_lu[0] - t_copy[0], flops / ((t_lu[0] - t_copy[0]) * 1e-3) / 1e12, launches, res, t_thin[0]))
+        print("n=%6d  system %.3f ms  lu+solve %.3f ms (%.2f TF/s, %d launches, backward error %.1e)  nullspace-cholesky fit %.3f ms (info %d, backward error %.1e)  thin(+256) %.3f ms"
+              % (n, t_sys[0], t_lu[0] - t_copy[0], flops / ((t_lu[0] - t_copy[0]) * 1e-3) / 1e12, launches, res, t_ns[0], int(info.item()), res_ns, t_thin[0]))
 
 
 if __name__ == "__main__":
