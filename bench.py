@@ -8,7 +8,8 @@ target are quoted on; it fits one GPU): per GPU 65536 lockstep DAMH chains, d=2,
 simple.json Gaussian problem, cubic RBF surrogate with 4096 centers, analytic toy G on the device,
 surrogate_is_updated=true: every 64 lockstep steps the new snapshots are compacted, all-gathered
 (NCCL), at most 256 of them enter the collector's refit (greedy thinning back to 4096 centers,
-saddle-point system build, LU with partial pivoting = solver_type 'direct'), the new coefficients
+saddle-point system build, dense direct solve: null-space projection + Cholesky, `--solver direct` selects
+the LU with partial pivoting that mirrors the reference's solver_type 'direct'), the new coefficients
 are broadcast and every chain switches to them.  Weak scaling: every GPU carries 65536 chains.
     cfg2: 4096 chains, frozen polynomial surrogate (degree 5)        (BASELINE.json configs[1])
     cfg5: 131072 chains/GPU, d=4, m=3, frozen cubic RBF 500 centers, frozen 2000-center RBF as G
@@ -40,7 +41,7 @@ DARCY = dict(prior_mean=0.0, prior_std=1.0, noise_std=[0.2, 0.1, 0.1], no_observ
 
 WORKLOADS = {
     "cfg3": dict(d=2, m=1, problem=SIMPLE, chains=65536, surrogate="rbf", centers=4096, kernel_type=1, updated=True,
-                 block=64, snapshots_per_refit=256, proposal_std=1.0, truth="toy",
+                 block=64, snapshots_per_refit=256, proposal_std=1.0, truth="toy", solver_type="nullspace",
                  name="illustrative-shape DAMH: 65536 chains/GPU, cubic RBF 4096 centers, surrogate_is_updated, refit every 64 steps"),
     "cfg2": dict(d=2, m=1, problem=SIMPLE, chains=4096, surrogate="poly", degree=5, updated=False, block=64,
                  proposal_std=1.0, truth="toy", name="simple.json-shape DAMH: 4096 chains, frozen poly degree 5"),
@@ -177,7 +178,8 @@ def build_models(w, rank_seed=0):
     updater = None
     if w["surrogate"] == "rbf":
         X, Y = training_set(w, w["centers"], 1)
-        updater = SR.Surrogate_update(d, m, kernel_type=w["kernel_type"], solver_type="direct", no_keep=w["centers"])
+        updater = SR.Surrogate_update(d, m, kernel_type=w["kernel_type"], solver_type=w.get("solver_type", "direct"),
+                                      no_keep=w["centers"])
         updater.add_arrays(X, Y)
         sur, _ = updater.update_device()
     else:
@@ -218,6 +220,8 @@ def run_ours(args):
         w["chains"] = args.chains
     if args.centers and w["surrogate"] == "rbf":
         w["centers"] = args.centers
+    if args.solver and w["surrogate"] == "rbf":
+        w["solver_type"] = args.solver
     d, m, C_, K = w["d"], w["m"], w["chains"], w["block"]
     updater, sur, truth, truth_SOL = build_models(w)
     SOL0 = sur.sol_numpy()
@@ -364,8 +368,8 @@ def run_ours(args):
         "config": {"workload": "%s: %s" % (args.workload, w["name"]), "chains_per_gpu": C_, "lockstep_steps_per_bench_step": K,
                    "no_parameters": d, "no_observations": m, "centers": n_c or None,
                    "l2": "256 MiB flush write before every bench step, inside the timed region",
-                   "refit": ("every %d steps: compact + all-gather + thin + LU(%d) + broadcast; %.2f ms avg inside the step"
-                             % (K, n_c + d + 1, float(np.mean(rf)))) if rf else "frozen surrogate"},
+                   "refit": ("every %d steps: compact + all-gather + thin + dense solve (%s, N=%d) + broadcast; %.2f ms avg inside the step"
+                             % (K, w.get("solver_type", "direct"), n_c + d + 1, float(np.mean(rf)))) if rf else "frozen surrogate"},
         "e2e": {"value": e2e_value, "unit": "chain steps/s", "h2d_bytes_per_step": int(pin_in.numel() * 8),
                 "d2h_bytes_per_step": int(pin_u.numel() * 8 + pin_c.numel() * 4), "steps": e2e_steps,
                 "ms_per_step": ms_e2e / e2e_steps},
@@ -445,6 +449,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--chains", type=int, default=0)
     ap.add_argument("--centers", type=int, default=0)
+    ap.add_argument("--solver", default="", choices=["", "direct", "nullspace"], help="dense solver of the RBF refit")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", type=int, default=0, help="run this many bench steps inside cudaProfilerStart/Stop and exit")

@@ -15,6 +15,7 @@
 #include <float.h>
 
 #include "sdb_gemm.cuh"
+#include "sdb_graph.cuh"
 
 #define NS_T 1024
 
@@ -131,43 +132,76 @@ __global__ void __launch_bounds__(256) ns_syr2_kernel(double *__restrict__ Phi, 
 // ---------------------------------------------------------------------------------------------------
 // Cholesky (lower, column-major, leading dimension ld) of the nb x nb matrix A, 64-column blocks
 // ---------------------------------------------------------------------------------------------------
+// 64 x 64 diagonal block in ONE CTA of 256 threads arranged 16 x 16; thread (ty, tx) keeps the 4 x 4 tile
+// rows 4ty.., columns 4tx.. in registers.  Per column: the diagonal owner publishes sqrt(a_jj), the owners of
+// column j publish the scaled column, everybody applies the rank-1 update to its tile: two barriers per column.
 __global__ void __launch_bounds__(256, 1) chol_potrf64_kernel(double *__restrict__ A, int64_t ld, int k0, int h, int *__restrict__ info) {
-    __shared__ double T[64][65];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < 64 * 64; e += 256) {
-        const int i = e & 63, c = e >> 6;
-        T[i][c] = (i < h && c <= i) ? A[(int64_t)(k0 + c) * ld + k0 + i] : 0.0;
-    }
-    __syncthreads();
-    for (int j = 0; j < h; ++j) {
-        const double djj = T[j][j];
-        if (!(djj > 0.0)) {                       // not positive definite (or NaN): report, keep going harmlessly
-            if (tid == 0 && *info == 0) *info = k0 + j + 1;
+    __shared__ double col[64];
+    __shared__ double dj_s;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    double a[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = ty * 4 + r, cc = tx * 4 + c;
+            a[r][c] = (i < h && cc <= i) ? A[(int64_t)(k0 + cc) * ld + k0 + i] : (i == cc ? 1.0 : 0.0);
         }
-        const double d = djj > 0.0 ? sqrt(djj) : 1.0;
-        const double rd = 1.0 / d;
-        __syncthreads();
-        if (tid == 0) T[j][j] = d;
-        for (int i = j + 1 + tid; i < h; i += 256) T[i][j] *= rd;
-        __syncthreads();
-        // trailing update of the lower triangle: (i, c), j < c <= i < h
-        const int rem = h - j - 1;
-        for (int e = tid; e < rem * rem; e += 256) {
-            const int i = j + 1 + e % rem, c = j + 1 + e / rem;
-            if (c <= i) T[i][c] = fma(-T[i][j], T[c][j], T[i][c]);
+    for (int jb = 0; jb < 16; ++jb) {            // column block; inside, the 4 columns are unrolled (static register indices)
+#pragma unroll
+        for (int jc = 0; jc < 4; ++jc) {
+            const int j = jb * 4 + jc;
+            if (j < h) {                          // uniform
+                if (tx == jb && ty == jb) {
+                    const double djj = a[jc][jc];
+                    if (!(djj > 0.0) && *info == 0) *info = k0 + j + 1;   // not positive definite (or NaN)
+                    dj_s = djj > 0.0 ? sqrt(djj) : 1.0;
+                }
+                __syncthreads();
+                const double d = dj_s, rd = 1.0 / d;
+                if (tx == jb) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int i = ty * 4 + r;
+                        double v = a[r][jc];
+                        v = i > j ? v * rd : (i == j ? d : 0.0);
+                        a[r][jc] = v;
+                        col[i] = v;
+                    }
+                }
+                __syncthreads();
+                if (tx >= jb) {
+                    double lr[4], lc[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) lr[r] = col[ty * 4 + r];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) lc[c] = col[tx * 4 + c];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (tx * 4 + c > j) a[r][c] = fma(-lr[r], lc[c], a[r][c]);
+                }
+            }
         }
-        __syncthreads();
     }
-    for (int e = tid; e < 64 * 64; e += 256) {
-        const int i = e & 63, c = e >> 6;
-        if (i < h && c <= i) A[(int64_t)(k0 + c) * ld + k0 + i] = T[i][c];
-    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = ty * 4 + r, cc = tx * 4 + c;
+            if (i < h && cc <= i) A[(int64_t)(k0 + cc) * ld + k0 + i] = a[r][c];
+        }
 }
 
-// L21 := A21 L11^{-T}: one thread per row of A21 (rows k0+h .. nb-1), the row in registers, L11 in shared memory
+// L21 := A21 L11^{-T}: one thread per row of A21 (rows k0+h .. nb-1).  The row lives in SHARED memory
+// (xs[c][thread], conflict-free) so the loops stay rolled: the fully unrolled register version was 2016 FMAs of
+// straight-line code and ran from the instruction cache's miss path.
 __global__ void __launch_bounds__(128) chol_trsm_kernel(double *__restrict__ A, int64_t ld, int k0, int h, int nb) {
     __shared__ double T[64][65];
     __shared__ double rdiag[64];
+    extern __shared__ __align__(16) double trsm_dyn[];
+    double (*xs)[128] = (double (*)[128])trsm_dyn;      // [64][128], 64 KB dynamic
     for (int e = threadIdx.x; e < 64 * 64; e += 128) {
         const int i = e & 63, c = e >> 6;
         T[i][c] = (i < h && c <= i) ? A[(int64_t)(k0 + c) * ld + k0 + i] : 0.0;
@@ -175,21 +209,21 @@ __global__ void __launch_bounds__(128) chol_trsm_kernel(double *__restrict__ A, 
     __syncthreads();
     if (threadIdx.x < 64) rdiag[threadIdx.x] = threadIdx.x < h ? 1.0 / T[threadIdx.x][threadIdx.x] : 1.0;
     __syncthreads();
-    const int r = k0 + h + blockIdx.x * 128 + threadIdx.x;
+    const int t = threadIdx.x;
+    const int r = k0 + h + blockIdx.x * 128 + t;
     if (r >= nb) return;
-    double x[64];
-#pragma unroll
-    for (int c = 0; c < 64; ++c) x[c] = c < h ? A[(int64_t)(k0 + c) * ld + r] : 0.0;
-#pragma unroll
-    for (int c = 0; c < 64; ++c) {
-        double t = x[c];
-#pragma unroll
-        for (int k = 0; k < c; ++k) t = fma(-x[k], T[c][k], t);
-        x[c] = t * rdiag[c];
+    for (int c = 0; c < h; ++c) xs[c][t] = A[(int64_t)(k0 + c) * ld + r];
+    for (int c = 0; c < h; ++c) {
+        double acc0 = xs[c][t], acc1 = 0.0;
+        int k = 0;
+        for (; k + 1 < c; k += 2) {
+            acc0 = fma(-xs[k][t], T[c][k], acc0);
+            acc1 = fma(-xs[k + 1][t], T[c][k + 1], acc1);
+        }
+        if (k < c) acc0 = fma(-xs[k][t], T[c][k], acc0);
+        xs[c][t] = (acc0 + acc1) * rdiag[c];
     }
-#pragma unroll
-    for (int c = 0; c < 64; ++c)
-        if (c < h) A[(int64_t)(k0 + c) * ld + r] = x[c];
+    for (int c = 0; c < h; ++c) A[(int64_t)(k0 + c) * ld + r] = xs[c][t];
 }
 
 // one warp per right-hand side: x = L11^{-1} b (TRANS = false) or L11^{-T} b (TRANS = true) on a block of h <= 64 rows
@@ -315,8 +349,13 @@ static int ns_enqueue(cudaStream_t st, double *S, int n, int d, int m, int kerne
         chol_potrf64_kernel<<<1, 256, 0, st>>>(A, ld, k0, h, d_info);
         const int rest = nb - k0 - h;
         if (rest > 0) {
+            static bool trsm_attr = false;
+            if (!trsm_attr) {
+                SDB_CUDA(cudaFuncSetAttribute((const void *)chol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 128 * 8));
+                trsm_attr = true;
+            }
             sdb_count_launch();
-            chol_trsm_kernel<<<(rest + 127) / 128, 128, 0, st>>>(A, ld, k0, h, nb);
+            chol_trsm_kernel<<<(rest + 127) / 128, 128, 64 * 128 * 8, st>>>(A, ld, k0, h, nb);
             double *L21 = A + (int64_t)k0 * ld + k0 + h;
             double *A22 = A + (int64_t)(k0 + h) * ld + k0 + h;
             int rc = sdb_syrk_k64_update(st, rest, rest, h, L21, L21, A22, ld);
@@ -372,7 +411,13 @@ extern "C" int sdb_rbf_fit_nullspace(const double *d_X, const double *d_Y, int64
     double *S = d_work;
     double *F = S + N * N;
     double *vec = F + N * m;
-    int rc = sdb_rbf_system(d_X, d_Y, n, d, m, kernel_type, S, F, stream);
-    if (rc) return rc;
-    return ns_enqueue((cudaStream_t)stream, S, (int)n, d, m, kernel_type, F, d_COEFS, vec, d_info);
+    cudaStream_t st = (cudaStream_t)stream;
+    auto enqueue = [&]() -> int {
+        int rc = sdb_rbf_system(d_X, d_Y, n, d, m, kernel_type, S, F, stream);
+        if (rc) return rc;
+        return ns_enqueue(st, S, (int)n, d, m, kernel_type, F, d_COEFS, vec, d_info);
+    };
+    if (n < 256) return enqueue();
+    sdb_graph_key key = {{d_X, d_Y, d_COEFS, d_work, d_info}, {n, d, m, kernel_type}, 2, 0};
+    return sdb_graph_run(st, key, enqueue);
 }

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 #include "sdb_gemm.cuh"
+#include "sdb_graph.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -570,24 +571,6 @@ static int lu_solve_factored(cudaStream_t st, const double *A, int64_t lda, int 
     return SDB_OK;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// The factorisation is a chain of a few thousand short, dependent kernels whose sequence depends only on
-// (N, nrhs) and whose arguments depend only on the buffer addresses; issuing them one by one is bound by
-// the host's launch rate (~12 us per launch measured), not by the GPU.  So the whole sequence is captured
-// once per (buffers, N, nrhs) into a CUDA graph and replayed afterwards.  SDB_LU_GRAPH=0 disables this.
-// ---------------------------------------------------------------------------------------------------
-struct lu_graph_entry {
-    const void *A, *B, *piv, *info;
-    int64_t N;
-    int nrhs, device;
-    cudaGraphExec_t exec;
-    unsigned long long last_use;
-};
-#define LU_GRAPH_SLOTS 8
-static lu_graph_entry g_lu_graphs[LU_GRAPH_SLOTS];
-static unsigned long long g_lu_tick = 0;
-static long long g_lu_graph_nodes = 0;
-
 static int lu_enqueue(cudaStream_t st, double *d_A, int64_t N, double *d_B, int nrhs, int32_t *d_piv, int32_t *d_info) {
     SDB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
     int rc = lu_factor(st, d_A, N, (int)N, d_piv, d_info);
@@ -596,78 +579,18 @@ static int lu_enqueue(cudaStream_t st, double *d_A, int64_t N, double *d_B, int 
     return rc;
 }
 
-static bool lu_graphs_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("SDB_LU_GRAPH");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v == 1;
-}
-
 // Factor A (column-major N x N, overwritten by L and U) and solve A X = B for nrhs columns
 // (B column-major N x nrhs, leading dimension N, overwritten by X).  d_piv: N ints.  d_info: 0, or
-// k+1 when U(k,k) is exactly zero (LAPACK's info).
+// k+1 when U(k,k) is exactly zero (LAPACK's info).  The kernel chain is replayed as a CUDA graph (sdb_graph.cuh).
 extern "C" int sdb_lu_solve(double *d_A, int64_t N, double *d_B, int32_t nrhs, int32_t *d_piv, int32_t *d_info,
                             void *stream) {
     SDB_CHECK_ARG(d_A && d_piv && d_info, "sdb_lu_solve: NULL pointer");
     SDB_CHECK_ARG(N >= 1 && N < (1 << 30), "sdb_lu_solve: N = %lld out of range", (long long)N);
     SDB_CHECK_ARG(nrhs >= 0 && (nrhs == 0 || d_B), "sdb_lu_solve: bad right-hand sides");
     cudaStream_t st = (cudaStream_t)stream;
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (st != nullptr) cudaStreamIsCapturing(st, &cs);
-    // small systems are not launch-bound enough to pay for an instantiation; the legacy default stream
-    // cannot be captured; a stream that is already being captured just records the kernels
-    if (!lu_graphs_enabled() || st == nullptr || cs != cudaStreamCaptureStatusNone || N < 256)
-        return lu_enqueue(st, d_A, N, d_B, nrhs, d_piv, d_info);
-    int dev = 0;
-    SDB_CUDA(cudaGetDevice(&dev));
-    lu_graph_entry *hit = nullptr, *victim = nullptr;
-    for (int i = 0; i < LU_GRAPH_SLOTS; ++i) {
-        lu_graph_entry &e = g_lu_graphs[i];
-        if (e.exec && e.A == d_A && e.B == d_B && e.piv == d_piv && e.info == d_info && e.N == N && e.nrhs == nrhs &&
-            e.device == dev) {
-            hit = &e;
-            break;
-        }
-    }
-    if (!hit) {
-        for (int i = 0; i < LU_GRAPH_SLOTS && !victim; ++i)
-            if (!g_lu_graphs[i].exec) victim = &g_lu_graphs[i];
-        if (!victim) {   // least recently used
-            victim = &g_lu_graphs[0];
-            for (int i = 1; i < LU_GRAPH_SLOTS; ++i)
-                if (g_lu_graphs[i].last_use < victim->last_use) victim = &g_lu_graphs[i];
-        }
-        // warm the lazily loaded kernels / attributes once outside the capture (first call in this process)
-        static bool warmed = false;
-        if (!warmed) {
-            warmed = true;
-            return lu_enqueue(st, d_A, N, d_B, nrhs, d_piv, d_info);
-        }
-        const long long before = sdb_launch_count(0);
-        cudaGraph_t graph = nullptr;
-        SDB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        int rc = lu_enqueue(st, d_A, N, d_B, nrhs, d_piv, d_info);
-        cudaError_t ce = cudaStreamEndCapture(st, &graph);
-        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-        if (ce != cudaSuccess) { sdb_set_error("sdb_lu_solve: graph capture failed: %s", cudaGetErrorString(ce)); return SDB_ERR_CUDA; }
-        if (victim->exec) cudaGraphExecDestroy(victim->exec);
-        victim->exec = nullptr;
-        cudaGraphExec_t exec = nullptr;
-        ce = cudaGraphInstantiate(&exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (ce != cudaSuccess) { sdb_set_error("sdb_lu_solve: graph instantiation failed: %s", cudaGetErrorString(ce)); return SDB_ERR_CUDA; }
-        g_lu_graph_nodes = sdb_launch_count(0) - before;
-        *victim = lu_graph_entry{d_A, d_B, d_piv, d_info, N, nrhs, dev, exec, 0};
-        hit = victim;
-    } else {
-        // replayed kernels are still launches of this library
-        for (long long k = 0; k < g_lu_graph_nodes; ++k) sdb_count_launch();
-    }
-    hit->last_use = ++g_lu_tick;
-    SDB_CUDA(cudaGraphLaunch(hit->exec, st));
-    return SDB_OK;
+    if (N < 256) return lu_enqueue(st, d_A, N, d_B, nrhs, d_piv, d_info);   // not launch-bound enough to pay for an instantiation
+    sdb_graph_key key = {{d_A, d_B, d_piv, d_info, nullptr}, {N, nrhs, 0, 0}, 1, 0};
+    return sdb_graph_run(st, key, [&]() { return lu_enqueue(st, d_A, N, d_B, nrhs, d_piv, d_info); });
 }
 
 // C (column-major, ldc) = beta C + alpha A B with generic strides (see sdb_gemm.cuh); nslab > 1 splits K

@@ -72,6 +72,7 @@ class Surrogate_update:
         self._new_par, self._new_obs = [], []
         self.last_info = None
         self._work = None                   # persistent scratch: stable addresses let the LU graph be replayed
+        self._io = None
         self._info_buf = torch.zeros((4,), dtype=torch.int32, device="cuda")
 
     @property
@@ -116,33 +117,42 @@ class Surrogate_update:
             self._thin(stream)
         n = self.no_processed = self._par.shape[0]
         N = n + d + 1
-        COEFS = torch.empty((N, m), dtype=torch.float64, device="cuda")
         info = self._info_buf
         info.zero_()
+        # persistent input / output / scratch buffers: stable addresses let the solvers replay their CUDA graphs
+        if self._io is None or self._io[0] != (n, d, m):
+            self._io = ((n, d, m), torch.empty((n, d), dtype=torch.float64, device="cuda"),
+                        torch.empty((n, m), dtype=torch.float64, device="cuda"),
+                        torch.empty((N, m), dtype=torch.float64, device="cuda"))
+        _, Xb, Yb, Cb = self._io
+        Xb.copy_(self._par)
+        Yb.copy_(self._obs)
+
+        def scratch(need):
+            if self._work is None or self._work.numel() < need:
+                self._work = torch.empty((need,), dtype=torch.float64, device="cuda")
+            return self._work
+
         done = False
         if self.solver_type == "nullspace" and int(self.kernel_type) in (0, 1, 4, 5, 6) and n > d + 1:
             # additive solver: null-space method + Cholesky (no pivoting); falls back to the pivoted LU below
             # if the projected kernel matrix is numerically not definite
-            need = L.lib().sdb_rbf_fit_nullspace_work(n, d, m)
-            if self._work is None or self._work.numel() < need:
-                self._work = torch.empty((need,), dtype=torch.float64, device="cuda")
-            L.check(L.lib().sdb_rbf_fit_nullspace(L.ptr(self._par), L.ptr(self._obs), n, d, m, int(self.kernel_type),
-                                                  L.ptr(COEFS), L.ptr(self._work), L.ptr(info), L.stream_handle(stream)))
+            work = scratch(L.lib().sdb_rbf_fit_nullspace_work(n, d, m))
+            L.check(L.lib().sdb_rbf_fit_nullspace(L.ptr(Xb), L.ptr(Yb), n, d, m, int(self.kernel_type), L.ptr(Cb), L.ptr(work),
+                                                  L.ptr(info), L.stream_handle(stream)))
             done = int(info[0].item()) == 0
             self.fallbacks = getattr(self, "fallbacks", 0) + (0 if done else 1)
         if done:
             pass
         elif self.solver_type in ("direct", "nullspace"):
-            need = L.lib().sdb_rbf_fit_work(n, d, m)
-            if self._work is None or self._work.numel() < need:
-                self._work = torch.empty((need,), dtype=torch.float64, device="cuda")
-            L.check(L.lib().sdb_rbf_fit(L.ptr(self._par), L.ptr(self._obs), n, d, m, int(self.kernel_type), L.ptr(COEFS),
-                                        L.ptr(self._work), L.ptr(info), L.stream_handle(stream)))
+            work = scratch(L.lib().sdb_rbf_fit_work(n, d, m))
+            L.check(L.lib().sdb_rbf_fit(L.ptr(Xb), L.ptr(Yb), n, d, m, int(self.kernel_type), L.ptr(Cb), L.ptr(work), L.ptr(info),
+                                        L.stream_handle(stream)))
         else:
             S = torch.empty((N, N), dtype=torch.float64, device="cuda")
             rhs = torch.empty((m, N), dtype=torch.float64, device="cuda")       # one contiguous column per observation
-            L.check(L.lib().sdb_rbf_system(L.ptr(self._par), L.ptr(self._obs), n, d, m, int(self.kernel_type), L.ptr(S),
-                                           L.ptr(rhs), L.stream_handle(stream)))
+            L.check(L.lib().sdb_rbf_system(L.ptr(Xb), L.ptr(Yb), n, d, m, int(self.kernel_type), L.ptr(S), L.ptr(rhs),
+                                           L.stream_handle(stream)))
             x = torch.zeros((m, N), dtype=torch.float64, device="cuda")
             x0 = None
             if self.initial_iteration is not None:
@@ -152,7 +162,8 @@ class Surrogate_update:
             for k in range(m):
                 L.check(L.lib().sdb_minres(L.ptr(S), N, L.ptr(rhs[k]), L.ptr(x0), L.ptr(x[k]), float(10.0 ** self.solver_tol_exp),
                                            maxiter, L.ptr(work), L.ptr(info), L.stream_handle(stream)))
-            COEFS.copy_(x.t())
+            Cb.copy_(x.t())
+        COEFS = Cb.clone()
         self._info = info
         mo = DeviceModel(L.MODEL_RBF, kernel_type=self.kernel_type, coefs=COEFS, centers=self._par.clone(), d=d, m=m)
         return mo, n
