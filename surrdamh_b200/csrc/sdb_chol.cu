@@ -136,8 +136,7 @@ __global__ void __launch_bounds__(256) ns_syr2_kernel(double *__restrict__ Phi, 
 // rows 4ty.., columns 4tx.. in registers.  Per column: the diagonal owner publishes sqrt(a_jj), the owners of
 // column j publish the scaled column, everybody applies the rank-1 update to its tile: two barriers per column.
 __global__ void __launch_bounds__(256, 1) chol_potrf64_kernel(double *__restrict__ A, int64_t ld, int k0, int h, int *__restrict__ info) {
-    __shared__ double col[64];
-    __shared__ double dj_s;
+    __shared__ double col[2][64];     // the UNSCALED column j, double-buffered: one barrier per column
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     double a[4][4];
 #pragma unroll
@@ -152,30 +151,29 @@ __global__ void __launch_bounds__(256, 1) chol_potrf64_kernel(double *__restrict
         for (int jc = 0; jc < 4; ++jc) {
             const int j = jb * 4 + jc;
             if (j < h) {                          // uniform
-                if (tx == jb && ty == jb) {
-                    const double djj = a[jc][jc];
-                    if (!(djj > 0.0) && *info == 0) *info = k0 + j + 1;   // not positive definite (or NaN)
-                    dj_s = djj > 0.0 ? sqrt(djj) : 1.0;
+                double *cj = col[j & 1];
+                if (tx == jb) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) cj[ty * 4 + r] = (ty * 4 + r >= j) ? a[r][jc] : 0.0;
                 }
                 __syncthreads();
-                const double d = dj_s, rd = 1.0 / d;
+                const double djj = cj[j];
+                const bool pd = djj > 0.0;
+                if (!pd && tid == 0 && *info == 0) *info = k0 + j + 1;      // not positive definite (or NaN)
+                const double rd = pd ? sdb_fast_rsqrt(djj) : 1.0;           // 1 / L(j, j)
                 if (tx == jb) {
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         const int i = ty * 4 + r;
-                        double v = a[r][jc];
-                        v = i > j ? v * rd : (i == j ? d : 0.0);
-                        a[r][jc] = v;
-                        col[i] = v;
+                        a[r][jc] = i > j ? a[r][jc] * rd : (i == j ? (pd ? djj * rd : 1.0) : 0.0);
                     }
                 }
-                __syncthreads();
                 if (tx >= jb) {
                     double lr[4], lc[4];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) lr[r] = col[ty * 4 + r];
+                    for (int r = 0; r < 4; ++r) lr[r] = cj[ty * 4 + r] * rd;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) lc[c] = col[tx * 4 + c];
+                    for (int c = 0; c < 4; ++c) lc[c] = cj[tx * 4 + c] * rd;
 #pragma unroll
                     for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -194,36 +192,37 @@ __global__ void __launch_bounds__(256, 1) chol_potrf64_kernel(double *__restrict
         }
 }
 
-// L21 := A21 L11^{-T}: one thread per row of A21 (rows k0+h .. nb-1).  The row lives in SHARED memory
-// (xs[c][thread], conflict-free) so the loops stay rolled: the fully unrolled register version was 2016 FMAs of
-// straight-line code and ran from the instruction cache's miss path.
-__global__ void __launch_bounds__(128) chol_trsm_kernel(double *__restrict__ A, int64_t ld, int k0, int h, int nb) {
-    __shared__ double T[64][65];
+// X = L11^{-1} (64 x 64 lower triangular) -> Xout column-major with leading dimension 64.  Four lanes share a
+// column: row i of X needs sum_k L(i, k) X(k, c), split over the lanes and combined with two shuffles; only those
+// four lanes ever read column c, so a warp-level sync per row suffices.  The panel's triangular solve then
+// becomes one DMMA multiplication L21 = A21 X^T (sdb_gemm_k64_inplace).
+__global__ void __launch_bounds__(256, 1) chol_trinv64_kernel(const double *__restrict__ A, int64_t ld, int k0, int h,
+                                                              double *__restrict__ Xout) {
+    // one 64 x 65 array holds both triangles: L(i, c) at Ls[i][c] (c <= i), X(k, c) at Ls[c][k + 1] (k >= c)
+    __shared__ double Ls[64][65];
     __shared__ double rdiag[64];
-    extern __shared__ __align__(16) double trsm_dyn[];
-    double (*xs)[128] = (double (*)[128])trsm_dyn;      // [64][128], 64 KB dynamic
-    for (int e = threadIdx.x; e < 64 * 64; e += 128) {
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 64 * 64; e += 256) {
         const int i = e & 63, c = e >> 6;
-        T[i][c] = (i < h && c <= i) ? A[(int64_t)(k0 + c) * ld + k0 + i] : 0.0;
+        if (c <= i) Ls[i][c] = (i < h) ? A[(int64_t)(k0 + c) * ld + k0 + i] : (i == c ? 1.0 : 0.0);
     }
     __syncthreads();
-    if (threadIdx.x < 64) rdiag[threadIdx.x] = threadIdx.x < h ? 1.0 / T[threadIdx.x][threadIdx.x] : 1.0;
+    if (tid < 64) rdiag[tid] = 1.0 / Ls[tid][tid];
     __syncthreads();
-    const int t = threadIdx.x;
-    const int r = k0 + h + blockIdx.x * 128 + t;
-    if (r >= nb) return;
-    for (int c = 0; c < h; ++c) xs[c][t] = A[(int64_t)(k0 + c) * ld + r];
-    for (int c = 0; c < h; ++c) {
-        double acc0 = xs[c][t], acc1 = 0.0;
-        int k = 0;
-        for (; k + 1 < c; k += 2) {
-            acc0 = fma(-xs[k][t], T[c][k], acc0);
-            acc1 = fma(-xs[k + 1][t], T[c][k + 1], acc1);
-        }
-        if (k < c) acc0 = fma(-xs[k][t], T[c][k], acc0);
-        xs[c][t] = (acc0 + acc1) * rdiag[c];
+    const int c = tid >> 2, part = tid & 3;
+    for (int i = 0; i < 64; ++i) {      // uniform trip count: the full-mask shuffles need every lane of the warp
+        double s = 0.0;
+        for (int k = c + part; k < i; k += 4) s = fma(Ls[i][k], Ls[c][k + 1], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (part == 0 && i >= c) Ls[c][i + 1] = ((i == c ? 1.0 : 0.0) - s) * rdiag[i];
+        __syncwarp();
     }
-    for (int c = 0; c < h; ++c) A[(int64_t)(k0 + c) * ld + r] = xs[c][t];
+    __syncthreads();
+    for (int e = tid; e < 64 * 64; e += 256) {
+        const int i = e & 63, cc = e >> 6;
+        Xout[cc * 64 + i] = (i < h && cc < h && cc <= i) ? Ls[cc][i + 1] : 0.0;
+    }
 }
 
 // one warp per right-hand side: x = L11^{-1} b (TRANS = false) or L11^{-T} b (TRANS = true) on a block of h <= 64 rows
@@ -259,6 +258,68 @@ __global__ void __launch_bounds__(256) chol_trsv_block_kernel(const double *__re
         }
         if (lane < h) b[lane] = x0;
         if (lane + 32 < h) b[lane + 32] = x1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Triangular solves with the inverses of the diagonal blocks (kept from the factorisation), one kernel per
+// 64-block and direction: every CTA forms the block's solution redundantly (a 64 x 64 mat-vec) and then
+// updates its own rows of the remaining right-hand side.
+//   forward : x_blk = Linv_k b_blk              -> X;   B[r] -= sum_k L(r, k0+k) x_k   for r >= k0 + h
+//   backward: y_blk = Linv_k^T w_blk            -> Y;   W[i] -= sum_k L(k0+k, i) y_k   for i <  k0
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chol_fwd_kernel(const double *__restrict__ A, int64_t ld, const double *__restrict__ Linv,
+                                                       double *__restrict__ B, double *__restrict__ X, int64_t ldb, int k0, int h,
+                                                       int nb, int m) {
+    __shared__ double bb[64], xs[64];
+    const int t = threadIdx.x;
+    for (int rhs = 0; rhs < m; ++rhs) {
+        double *b = B + (int64_t)rhs * ldb;
+        if (t < 64) bb[t] = t < h ? b[k0 + t] : 0.0;
+        __syncthreads();
+        if (t < 64) {
+            double s = 0.0;
+            for (int k = 0; k <= t && k < h; ++k) s = fma(Linv[k * 64 + t], bb[k], s);
+            xs[t] = t < h ? s : 0.0;
+            if (blockIdx.x == 0 && t < h) X[(int64_t)rhs * ldb + k0 + t] = s;
+        }
+        __syncthreads();
+        const int r = k0 + h + blockIdx.x * 256 + t;
+        if (r < nb) {
+            double acc = 0.0;
+#pragma unroll 8
+            for (int k = 0; k < h; ++k) acc = fma(A[(int64_t)(k0 + k) * ld + r], xs[k], acc);
+            b[r] -= acc;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) chol_bwd_kernel(const double *__restrict__ A, int64_t ld, const double *__restrict__ Linv,
+                                                       double *__restrict__ W, double *__restrict__ Y, int64_t ldb, int k0, int h,
+                                                       int m) {
+    __shared__ double wb[64], ys[64];
+    const int t = threadIdx.x;
+    for (int rhs = 0; rhs < m; ++rhs) {
+        double *w = W + (int64_t)rhs * ldb;
+        if (t < 64) wb[t] = t < h ? w[k0 + t] : 0.0;
+        __syncthreads();
+        if (t < 64) {
+            double s = 0.0;
+            for (int k = t; k < h; ++k) s = fma(Linv[t * 64 + k], wb[k], s);      // Linv^T(t, k) = Linv(k, t)
+            ys[t] = t < h ? s : 0.0;
+            if (blockIdx.x == 0 && t < h) Y[(int64_t)rhs * ldb + k0 + t] = s;
+        }
+        __syncthreads();
+        const int i = blockIdx.x * 256 + t;
+        if (i < k0) {
+            const double *a = A + (int64_t)i * ld + k0;        // L(k0 + k, i), contiguous in k
+            double acc = 0.0;
+#pragma unroll 8
+            for (int k = 0; k < h; ++k) acc = fma(a[k], ys[k], acc);
+            w[i] -= acc;
+        }
+        __syncthreads();
     }
 }
 
@@ -323,6 +384,8 @@ static int ns_enqueue(cudaStream_t st, double *S, int n, int d, int m, int kerne
     const int64_t ld = N;
     double *P = S + (int64_t)n * ld;
     double *tau = vec, *v = vec + 64, *w = v + n, *z = w + n;
+    double *xf = z + n;                                   // forward-solve result, m columns of length ld
+    double *xinv_all = xf + (int64_t)m * ld;              // inverse of every 64 x 64 diagonal block
     const double sgn = (kernel_type == 0 || kernel_type == 6) ? -1.0 : 1.0;
     SDB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
     sdb_count_launch();
@@ -348,43 +411,33 @@ static int ns_enqueue(cudaStream_t st, double *S, int n, int d, int m, int kerne
         sdb_count_launch();
         chol_potrf64_kernel<<<1, 256, 0, st>>>(A, ld, k0, h, d_info);
         const int rest = nb - k0 - h;
+        double *xinv = xinv_all + (int64_t)(k0 / 64) * 4096;
+        sdb_count_launch();
+        chol_trinv64_kernel<<<1, 256, 0, st>>>(A, ld, k0, h, xinv);
         if (rest > 0) {
-            static bool trsm_attr = false;
-            if (!trsm_attr) {
-                SDB_CUDA(cudaFuncSetAttribute((const void *)chol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 128 * 8));
-                trsm_attr = true;
-            }
-            sdb_count_launch();
-            chol_trsm_kernel<<<(rest + 127) / 128, 128, 64 * 128 * 8, st>>>(A, ld, k0, h, nb);
             double *L21 = A + (int64_t)k0 * ld + k0 + h;
+            // L21 = A21 L11^{-T}:  (A21 X^T)(r, j) = sum_k A21(r, k) X(j, k),  X(j, k) = xinv[k*64 + j]
+            int rc2 = sdb_gemm_k64_inplace(st, rest, h, L21, ld, xinv, 64);
+            if (rc2) return rc2;
             double *A22 = A + (int64_t)(k0 + h) * ld + k0 + h;
             int rc = sdb_syrk_k64_update(st, rest, rest, h, L21, L21, A22, ld);
             if (rc) return rc;
         }
     }
-    // (s B22) y2 = s g2: forward with L, backward with L^T, m right-hand sides living in F[q:n]
+    // (s B22) y2 = s g2: forward with L, backward with L^T; right-hand sides in F[q:n], result back in F[q:n]
     double *G2 = F + q;
-    const int tb = (m + 7) / 8;
     for (int k0 = 0; k0 < nb; k0 += 64) {
         const int h = (nb - k0) < 64 ? (nb - k0) : 64;
-        sdb_count_launch();
-        chol_trsv_block_kernel<false><<<tb, 256, 0, st>>>(A, ld, G2, ld, k0, h, m);
         const int rest = nb - k0 - h;
-        if (rest > 0) {
-            int rc = sdb_gemm(st, rest, m, h, -1.0, A + (int64_t)k0 * ld + k0 + h, 1, ld, G2 + k0, 1, ld, 1.0, G2 + k0 + h, ld);
-            if (rc) return rc;
-        }
-    }
-    for (int k1 = nb; k1 > 0;) {
-        const int h = (k1 % 64) ? (k1 % 64) : 64;
-        const int k0 = k1 - h;
         sdb_count_launch();
-        chol_trsv_block_kernel<true><<<tb, 256, 0, st>>>(A, ld, G2, ld, k0, h, m);
-        if (k0 > 0) {   // w[0:k0] -= L[k0:k0+h, 0:k0]^T y_block
-            int rc = sdb_gemm(st, k0, m, h, -1.0, A + k0, ld, 1, G2 + k0, 1, ld, 1.0, G2, ld);
-            if (rc) return rc;
-        }
-        k1 = k0;
+        chol_fwd_kernel<<<rest > 0 ? (rest + 255) / 256 : 1, 256, 0, st>>>(A, ld, xinv_all + (int64_t)(k0 / 64) * 4096, G2, xf, ld, k0,
+                                                                           h, nb, m);
+    }
+    for (int k0 = ((nb - 1) / 64) * 64; k0 >= 0; k0 -= 64) {
+        const int h = (nb - k0) < 64 ? (nb - k0) : 64;
+        sdb_count_launch();
+        chol_bwd_kernel<<<k0 > 0 ? (k0 + 255) / 256 : 1, 256, 0, st>>>(A, ld, xinv_all + (int64_t)(k0 / 64) * 4096, xf, G2, ld, k0, h,
+                                                                       m);
     }
     sdb_count_launch();
     ns_finish_kernel<<<m, NS_T, 0, st>>>(S, ld, n, q, tau, F, ld, m, COEFS);
@@ -394,7 +447,8 @@ static int ns_enqueue(cudaStream_t st, double *S, int n, int d, int m, int kerne
 
 extern "C" int64_t sdb_rbf_fit_nullspace_work(int64_t n, int32_t d, int32_t m) {
     const int64_t N = n + d + 1;
-    return N * N + N * m + 3 * n + 128;   // system | right-hand sides | tau, v, w, z
+    // system | right-hand sides | tau, v, w, z | forward-solve result | inverses of the diagonal blocks
+    return N * N + N * m + 3 * n + 128 + N * m + (n / 64 + 2) * 4096;
 }
 
 // Same contract as sdb_rbf_fit (X [n x d], Y [n x m] -> d_COEFS [(n+d+1) x m] row-major) for kernel types

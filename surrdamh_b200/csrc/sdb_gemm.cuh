@@ -196,9 +196,11 @@ __device__ __forceinline__ void sdb_cp_async8(void *smem, const void *gmem, bool
 // BT = false: B(k, j) = B[j*ld + k]  (k-contiguous: the U12 block of the LU);  shared layout Bs[n][k]
 // BT = true : B(k, j) = B[k*ld + j]  (j-contiguous: B = L21^T of the Cholesky SYRK); shared layout Bs[k][n]
 // LOWER: tiles strictly above the diagonal are skipped (symmetric rank-k update of the lower triangle)
-template <bool BT, bool LOWER>
+// ASSIGN: C = A B instead of C -= A B (C may alias A when N <= 64: a CTA reads its whole A tile before it stores)
+template <bool BT, bool LOWER, bool ASSIGN>
 static __global__ void __launch_bounds__(256, 2) sdb_gemm_k64_kernel(const double *__restrict__ A, const double *__restrict__ B,
-                                                                     double *__restrict__ C, int64_t ld, int M, int N, int K) {
+                                                                     double *__restrict__ C, int64_t ld, int64_t ldb, int M, int N,
+                                                                     int K) {
     const int m0 = blockIdx.x * GM_BM, n0 = blockIdx.y * GM_BN;
     if (LOWER && n0 > m0 + GM_BM - 1) return;
     extern __shared__ __align__(16) double gk_sm[];
@@ -228,11 +230,11 @@ static __global__ void __launch_bounds__(256, 2) sdb_gemm_k64_kernel(const doubl
             if (!BT) {
                 const int kk = kb + (idx & 31), nn = idx >> 5;
                 const bool ok = (n0 + nn < N) && (kk < K);
-                sdb_cp_async8(&Bs[nn][kk], B + (int64_t)(n0 + nn) * ld + kk, ok);
+                sdb_cp_async8(&Bs[nn][kk], B + (int64_t)(n0 + nn) * ldb + kk, ok);
             } else {
                 const int nn = idx & 63, kk = kb + (idx >> 6);
                 const bool ok = (n0 + nn < N) && (kk < K);
-                sdb_cp_async8(&Bt[kk][nn], B + (int64_t)kk * ld + (n0 + nn), ok);
+                sdb_cp_async8(&Bt[kk][nn], B + (int64_t)kk * ldb + (n0 + nn), ok);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -272,24 +274,25 @@ static __global__ void __launch_bounds__(256, 2) sdb_gemm_k64_kernel(const doubl
                 const int gm = m0 + wm + i * 8 + gid, gn = n0 + wn + j * 8 + tig * 2 + e;
                 if (gm < M && gn < N) {
                     double *p = C + (int64_t)gn * ld + gm;
-                    *p -= acc[i][j][e];
+                    if (ASSIGN) *p = acc[i][j][e];
+                    else *p -= acc[i][j][e];
                 }
             }
 }
 
-template <bool BT, bool LOWER>
+template <bool BT, bool LOWER, bool ASSIGN>
 static inline int sdb_gemm_k64_launch(cudaStream_t st, int M, int N, int K, const double *A, const double *B, double *C,
-                                      int64_t ld) {
+                                      int64_t ld, int64_t ldb) {
     if (M <= 0 || N <= 0 || K <= 0) return SDB_OK;
     const int smem = (GK_K * (GM_BM + GK_APAD) + GK_K * (GM_BN + GK_APAD)) * 8;
     static bool attr_set = false;
     if (!attr_set) {
-        SDB_CUDA(cudaFuncSetAttribute((const void *)sdb_gemm_k64_kernel<BT, LOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SDB_CUDA(cudaFuncSetAttribute((const void *)sdb_gemm_k64_kernel<BT, LOWER, ASSIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     dim3 grid((M + GM_BM - 1) / GM_BM, (N + GM_BN - 1) / GM_BN);
     sdb_count_launch();
-    sdb_gemm_k64_kernel<BT, LOWER><<<grid, 256, smem, st>>>(A, B, C, ld, M, N, K);
+    sdb_gemm_k64_kernel<BT, LOWER, ASSIGN><<<grid, 256, smem, st>>>(A, B, C, ld, ldb, M, N, K);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
 }
@@ -297,10 +300,15 @@ static inline int sdb_gemm_k64_launch(cudaStream_t st, int M, int N, int K, cons
 // C -= A B, B = U12 (k-contiguous): the LU trailing update
 static inline int sdb_gemm_k64_update(cudaStream_t st, int M, int N, int K, const double *A, const double *B, double *C,
                                       int64_t ld) {
-    return sdb_gemm_k64_launch<false, false>(st, M, N, K, A, B, C, ld);
+    return sdb_gemm_k64_launch<false, false, false>(st, M, N, K, A, B, C, ld, ld);
 }
 // lower(C) -= A A2^T with A2 given as rows (B(k, j) = A2[k*ld + j]): the Cholesky trailing update
 static inline int sdb_syrk_k64_update(cudaStream_t st, int M, int N, int K, const double *A, const double *A2, double *C,
                                       int64_t ld) {
-    return sdb_gemm_k64_launch<true, true>(st, M, N, K, A, A2, C, ld);
+    return sdb_gemm_k64_launch<true, true, false>(st, M, N, K, A, A2, C, ld, ld);
+}
+// A (M x K, leading dimension ld) := A * Xt with Xt(k, j) = X[k*ldx + j], K, N <= 64: the triangular solve of the
+// Cholesky panel as a multiplication by the inverse of the diagonal block, in place
+static inline int sdb_gemm_k64_inplace(cudaStream_t st, int M, int K, double *A, int64_t ld, const double *X, int64_t ldx) {
+    return sdb_gemm_k64_launch<true, false, true>(st, M, K, K, A, X, A, ld, ldx);
 }
