@@ -139,7 +139,7 @@ def cpu_baseline(wname, SOL, truth_SOL, seconds, cores=None):
 # ----------------------------------------------------------------------------------------------------
 def clocks_monitor_start(path):
     q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
     try:
         return subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
                                 stdout=open(path, "w"), stderr=subprocess.DEVNULL)
@@ -147,7 +147,10 @@ def clocks_monitor_start(path):
         return None
 
 
-def clocks_summary(path, gpu_index):
+def clocks_summary(path, gpu_index, t0=None, t1=None):
+    """Median SM clock and throttle reasons of the samples taken between wall-clock times t0 and t1 (the timed
+    region; the monitor itself runs from before the warm-up so that it is sampling by then)."""
+    import datetime
     sm, mx, reasons = [], 0.0, set()
     names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
     try:
@@ -155,6 +158,13 @@ def clocks_summary(path, gpu_index):
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9 or f[0] != str(gpu_index):
                 continue
+            if t0 is not None and len(f) >= 10:
+                try:
+                    ts = datetime.datetime.strptime(f[9], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if ts < t0 - 0.1 or ts > t1 + 0.1:
+                        continue
+                except ValueError:
+                    pass
             try:
                 sm.append(float(f[1])); mx = max(mx, float(f[2]))
             except ValueError:
@@ -291,6 +301,8 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    clk_path = os.path.join(tempfile.gettempdir(), "sdb_clocks_%d.csv" % os.getpid())
+    mon = clocks_monitor_start(clk_path) if (rank == 0 and not args.profile) else None
     blk.prepare("DAMH", sur, truth)
     for _ in range(max(args.warmup, 3)):
         one_block(False)
@@ -317,10 +329,10 @@ def run_ours(args):
     fp64_peak_tf = pb * 256 * 8 * 2.0 * iters / (p0.elapsed_time(p1) * 1e-3) / 1e12
 
     # ---- timed: device-resident --------------------------------------------------------------------------
-    clk_path = os.path.join(tempfile.gettempdir(), "sdb_clocks_%d.csv" % os.getpid())
-    mon = clocks_monitor_start(clk_path) if rank == 0 else None
     L.lib().sdb_launch_count(1)
+    wall0 = time.time()
     ms_total = timed_region(args.steps)
+    wall1 = time.time()
     launches = int(L.lib().sdb_launch_count(1))
     if mon is not None:
         mon.terminate()
@@ -375,12 +387,16 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / e2e_steps},
         "gpu_launches": launches,
         "roofline": {"bound": "fp64-pipe", "achieved": achieved_tf, "peak": fp64_peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / fp64_peak_tf, "traffic": None, "kernel": "chain_kernel<%d,%d>" % (d, m),
+                     "frac": achieved_tf / fp64_peak_tf,
+                     "traffic": 120953344 if args.workload == "cfg3" and not args.chains and not args.centers else None,
+                     "traffic_note": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the ncu --set full capture "
+                                     "in profiles/r01_chain_kernel_ncu.md; algorithmic bytes = C*K*25 B trace + state = 1.05e8",
+                     "kernel": "chain_kernel<%d,%d>" % (d, m),
                      "kernel_ms": avg_ms, "kernel_share_of_step": avg_ms * len(kern) / ms_total,
                      "flops_per_launch": flops_launch,
                      "peak_source": "sdb_fp64_probe (8 independent DFMA chains/thread), measured live in this run; "
                                     "MEASURED_PEAKS.json has no FP64 entry"},
-        "clocks": clocks_summary(clk_path, local),
+        "clocks": clocks_summary(clk_path, local, wall0, wall1),
     }
     if cpu is not None:
         out["cpu_baseline"] = cpu

@@ -154,6 +154,9 @@ typedef struct sdb_chain_args {
     double *snap_obs; /* DEVICE [K][m][C]: its G */
     /* split phases: G of the proposals supplied by the host for DECIDE */
     const double *G_prop; /* DEVICE [m][C] */
+    /* optional trace: surrogate log posterior of the CURRENT sample as used by step k (the
+     * pre_posterior_current_sample the reference writes into its data rows); 0 for MH */
+    double *pre_cur;      /* DEVICE [K][C], may be NULL */
 } sdb_chain_args;
 
 /* ---- library ------------------------------------------------------------------------- */

@@ -25,6 +25,7 @@ class Trace:
         self.prop = torch.empty((K, d, C_), dtype=torch.float64, device=device) if full else None
         self.post = torch.empty((K, C_), dtype=torch.float64, device=device) if full else None
         self.pre = torch.empty((K, C_), dtype=torch.float64, device=device) if full else None
+        self.pre_cur = torch.empty((K, C_), dtype=torch.float64, device=device) if full else None
         self.snap_par = torch.empty((K, d, C_), dtype=torch.float64, device=device) if snapshots else None
         self.snap_obs = torch.empty((K, m, C_), dtype=torch.float64, device=device) if snapshots else None
 
@@ -192,6 +193,7 @@ class ChainBlock:
                              % (trace.K, trace.C, K, self.C))
         a.flags, a.prop, a.post, a.pre = L.ptr(trace.flags), L.ptr(trace.prop), L.ptr(trace.post), L.ptr(trace.pre)
         a.snap_par, a.snap_obs = L.ptr(trace.snap_par), L.ptr(trace.snap_obs)
+        a.pre_cur = L.ptr(trace.pre_cur)
         self._trace = trace
 
     # ---- results ---------------------------------------------------------------------------------

@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, c
             uni0 = sdb_u01(b.x, b.y);
             uni1 = sdb_u01(b.z, b.w);
         }
+        if (a.pre_cur && writer && a.phase != SDB_PHASE_DECIDE) a.pre_cur[row] = pre_u;
         bool pass1;
         if (a.phase != SDB_PHASE_DECIDE) {
             // ---- proposal: u' = u + sigma*z, separately rounded (numpy: loc + scale*gauss) -------

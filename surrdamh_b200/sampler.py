@@ -124,6 +124,8 @@ class LockstepSampler:
             blk.prepare(kind, surrogate, self.truth)
         else:
             blk.prepare(kind, surrogate, None, G_host=self._host_G(blk.current_numpy()))
+        if hasattr(self.trace_sink, "begin_stage"):
+            self.trace_sink.begin_stage(i, st, self)
         R = self.conf.refit_every if collects else min(n_steps, 1024)
         refits0 = col.no_refits if col is not None else 0
         done, swapped = 0, False
@@ -151,6 +153,8 @@ class LockstepSampler:
             if time.time() - t0 > time_limit:
                 break
         torch.cuda.synchronize(self.device)
+        if hasattr(self.trace_sink, "end_stage"):
+            self.trace_sink.end_stage(i, st, self, done)
         res = StageResult(i, kind, done, blk.counters_numpy(), time.time() - t0, (col.no_refits - refits0) if col is not None else 0)
         self.results.append(res)
         return res
@@ -180,6 +184,7 @@ class LockstepSampler:
                 trace.flags[k] = one.flags[0]
                 if trace.prop is not None:
                     trace.prop[k], trace.post[k], trace.pre[k] = one.prop[0], one.post[0], one.pre[0]
+                    trace.pre_cur[k] = one.pre_cur[0]
                 if collects:
                     trace.snap_par[k], trace.snap_obs[k] = one.snap_par[0], one.snap_obs[0]
 

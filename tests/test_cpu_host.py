@@ -43,7 +43,7 @@ def test_struct_layouts_match_header_sizes():
 #include "surrdamh_b200.h"
 int main(void) {
   printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(sdb_model), sizeof(sdb_problem), sizeof(sdb_chain_state), sizeof(sdb_chain_args),
-         offsetof(sdb_chain_args, state), offsetof(sdb_chain_args, seed), offsetof(sdb_chain_args, G_prop));
+         offsetof(sdb_chain_args, state), offsetof(sdb_chain_args, seed), offsetof(sdb_chain_args, pre_cur));
   return 0; }
 '''
     with tempfile.TemporaryDirectory() as t:
@@ -53,7 +53,7 @@ int main(void) {
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         got = [int(x) for x in subprocess.check_output([exe]).split()]
     want = [ctypes.sizeof(_lib.Model), ctypes.sizeof(_lib.Problem), ctypes.sizeof(_lib.ChainState), ctypes.sizeof(_lib.ChainArgs),
-            _lib.ChainArgs.state.offset, _lib.ChainArgs.seed.offset, _lib.ChainArgs.G_prop.offset]
+            _lib.ChainArgs.state.offset, _lib.ChainArgs.seed.offset, _lib.ChainArgs.pre_cur.offset]
     assert got == want
 
 

@@ -130,3 +130,41 @@ def test_full_gpu_pipeline_matches_oracle_in_distribution():
     assert np.all(np.abs(mean_g - mean_o) < 0.5), (mean_g, mean_o)
     assert np.all(np.abs(np.sqrt(np.diag(cov_g)) - np.sqrt(np.diag(cov_o))) < 0.5), (cov_g, cov_o)
     assert smp.collector.no_refits == 2 + 20
+
+
+def test_csv_traces_match_reference_files(tmp_path):
+    """The on-disk layout of classes_SAMPLER.py written from the GPU trace: data/ (compressed chain rows),
+    raw_data/ (per-step labels), notes/, DAMH_accepted/ and DAMH_rejected/ equal what the reference's own
+    Algorithm objects wrote in the golden run (weights and samples exact, log-posteriors to 1e-9)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import csv
+    from surrdamh_b200.sampler import LockstepSampler
+    from surrdamh_b200.trace_csv import CsvTraceWriter
+    g = load("simple_lockstep")
+    N, R, total = [int(x) for x in g["meta"]]
+    hist = g["history"]
+    conf = _conf({"refit_every": R, "saved_samples_name": "csvtest"})
+    sink = CsvTraceWriter("csvtest", root=str(tmp_path))
+    smp = LockstepSampler(conf, no_chains=N, streams=_streams_for(N, SIMPLE_CONF, "cuda"), trace_sink=sink)
+    smp.collector.refit_hook = lambda par, obs, k: [g["SOL_%d" % k], int(hist[k][2])]
+    res = smp.run()
+    base = tmp_path / "saved_samples" / "csvtest"
+    code = {"prerejected": 0, "accepted": 1, "rejected": 2}
+    for i, st in enumerate(SIMPLE_CONF["samplers_list"]):
+        for c in range(N):
+            name = "alg%03d%s_rank%d" % (i, st["type"], c)
+            rows = np.array([[float(x) for x in r] for r in csv.reader(open(base / "data" / (name + ".csv")))])
+            want = g[f"st{i}_c{c}_data"]
+            assert rows.shape == want.shape, (i, c)
+            assert np.array_equal(rows[:, :3], want[:, :3])
+            assert close(rows[:, 3:], want[:, 3:], rtol=1e-9), (i, c)
+            raw = [r for r in csv.reader(open(base / "raw_data" / (name + ".csv")))]
+            assert np.array_equal(np.array([code[r[0]] for r in raw], dtype=np.uint8), g[f"st{i}_c{c}_flags"])
+            notes = [r for r in csv.reader(open(base / "notes" / (name + ".csv")))]
+            assert notes[0][0] == "name" and notes[1][0] == name
+            assert [int(notes[1][2]), int(notes[1][3]), int(notes[1][4])] == list(g[f"st{i}_c{c}_counters"])
+            if st["type"] == "DAMH":
+                acc = [r for r in csv.reader(open(base / "DAMH_accepted" / (name + ".csv")))]
+                rej = [r for r in csv.reader(open(base / "DAMH_rejected" / (name + ".csv")))]
+                assert len(acc) == g[f"st{i}_c{c}_counters"][0] and len(rej) == g[f"st{i}_c{c}_counters"][1]
