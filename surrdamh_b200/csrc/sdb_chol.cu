@@ -404,8 +404,18 @@ static int ns_enqueue(cudaStream_t st, double *S, int n, int d, int m, int kerne
         sdb_count_launch();
         ns_scale_rhs_kernel<<<148, 256, 0, st>>>(F, ld, q, n, m, sgn);
     }
-    // Cholesky of B22 = S[q:n, q:n]
+    // Cholesky of B22 = S[q:n, q:n], right-looking with a look-ahead of one panel: after the triangular solve
+    // of panel k the trailing update is split into the 64 columns of panel k+1 (main stream) and the rest (side
+    // stream); panel k+1 is factored on the main stream while the rest of update k is still running.
     double *A = S + (int64_t)q * ld + q;
+    static cudaStream_t aux = nullptr;
+    static cudaEvent_t ev_trsm = nullptr, ev_rest = nullptr;
+    if (!aux) {
+        SDB_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+        SDB_CUDA(cudaEventCreateWithFlags(&ev_trsm, cudaEventDisableTiming));
+        SDB_CUDA(cudaEventCreateWithFlags(&ev_rest, cudaEventDisableTiming));
+    }
+    bool rest_pending = false;   // a side-stream update whose completion the main stream has not yet waited for
     for (int k0 = 0; k0 < nb; k0 += 64) {
         const int h = (nb - k0) < 64 ? (nb - k0) : 64;
         sdb_count_launch();
@@ -420,10 +430,22 @@ static int ns_enqueue(cudaStream_t st, double *S, int n, int d, int m, int kerne
             int rc2 = sdb_gemm_k64_inplace(st, rest, h, L21, ld, xinv, 64);
             if (rc2) return rc2;
             double *A22 = A + (int64_t)(k0 + h) * ld + k0 + h;
-            int rc = sdb_syrk_k64_update(st, rest, rest, h, L21, L21, A22, ld);
+            const int nxt = rest < 64 ? rest : 64;      // columns of the next panel
+            // the previous side-stream update also wrote into the columns touched from here on
+            if (rest_pending) { SDB_CUDA(cudaStreamWaitEvent(st, ev_rest, 0)); rest_pending = false; }
+            SDB_CUDA(cudaEventRecord(ev_trsm, st));
+            int rc = sdb_gemm_k64_launch<true, false, false>(st, rest, nxt, h, L21, L21, A22, ld, ld);     // next panel's columns
             if (rc) return rc;
+            if (rest > 64) {
+                SDB_CUDA(cudaStreamWaitEvent(aux, ev_trsm, 0));
+                rc = sdb_syrk_k64_update(aux, rest - 64, rest - 64, h, L21 + 64, L21 + 64, A22 + (int64_t)64 * ld + 64, ld);
+                if (rc) return rc;
+                SDB_CUDA(cudaEventRecord(ev_rest, aux));
+                rest_pending = true;
+            }
         }
     }
+    if (rest_pending) SDB_CUDA(cudaStreamWaitEvent(st, ev_rest, 0));
     // (s B22) y2 = s g2: forward with L, backward with L^T; right-hand sides in F[q:n], result back in F[q:n]
     double *G2 = F + q;
     for (int k0 = 0; k0 < nb; k0 += 64) {
