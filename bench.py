@@ -224,6 +224,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if not os.environ.get("SDB_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout, which carries the JSON line
         dist.init_process_group("nccl", device_id=dev)
     w = dict(WORKLOADS[args.workload])
     if args.chains:
