@@ -251,26 +251,45 @@ def run_ours(args):
         col = Collector(updater if (rank == 0 or world == 1) else None, "rbf", d, m, kernel_type=w["kernel_type"], rank=rank,
                         world=world, snapshots_per_refit=w["snapshots_per_refit"], refit_mode="broadcast", device=dev)
         col.model = sur
-    trace = Trace(K, C_, d, m, dev, snapshots=w["updated"], full=False) if w["updated"] else None
+    overlap = bool(w["updated"]) and args.overlap
+    traces = [Trace(K, C_, d, m, dev, snapshots=True, full=False) for _ in range(2 if overlap else 1)] if w["updated"] else [None]
+    acol = None
+    if overlap:
+        from surrdamh_b200.collector import AsyncCollector
+        acol = AsyncCollector(col, dev)
     flush = torch.empty((256 << 20) // 8, dtype=torch.float64, device=dev)      # > 126 MB of L2
-    model = {"sur": sur, "swapped": False}
+    model = {"sur": sur, "swapped": False, "b": 0, "drained": 0}
     kern_ms, refit_ms = [], []
     ev_pool = []
 
     def one_block(timed, host_io=None):
-        """One bench step.  host_io = (pinned_in, pinned_out_u, pinned_out_cnt): the e2e variant."""
+        """One bench step.  host_io = (pinned_in, pinned_out_u, pinned_out_cnt): the e2e variant.
+        With the asynchronous collector the snapshots of block b are refitted on the side stream while block b+1
+        runs, and the surrogate of round b is switched in at the start of block b+2."""
+        b = model["b"]
+        model["b"] += 1
+        main = torch.cuda.current_stream()
+        if acol is not None and b >= 2:
+            R, new = acol.result(b - 2)
+            main.wait_event(R)
+            acol.forget(b - 2)
+            if new is not None:
+                model["sur"], model["swapped"] = new, True
+        trace = traces[b % len(traces)]
         flush.fill_(1.0)
         if host_io is not None:
             blk.u.copy_(host_io[0], non_blocking=True)                      # H2D: chain samples from pinned host memory
             blk.prepare("DAMH", model["sur"], truth)                         # G(u), posteriors of the uploaded samples
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        blk.run("DAMH", K, prop, model["sur"], truth, trace=trace, refresh_pre=model["swapped"])
+        blk.run("DAMH", K, prop, model["sur"], truth, trace=trace, refresh_pre=model["swapped"], coresident=acol is not None)
         e1.record()
         if timed:
             ev_pool.append((e0, e1, model["swapped"]))
         model["swapped"] = False
-        if col is not None:
+        if acol is not None:
+            acol.submit(b, trace, K, w["snapshots_per_refit"], e1, blk.step0, timed)
+        elif col is not None:
             r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             r0.record()
             par, obs, cnt = compact_snapshots(trace, K, w["snapshots_per_refit"])
@@ -284,7 +303,18 @@ def run_ours(args):
             host_io[2].copy_(blk.counters, non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
+    def drain():
+        """Make the sampling stream wait for every collector round issued so far (their surrogates stay queued)."""
+        if acol is None:
+            return
+        main = torch.cuda.current_stream()
+        for b in range(max(model["drained"], model["b"] - 2), model["b"]):
+            R, _ = acol.result(b)
+            main.wait_event(R)
+        model["drained"] = model["b"]
+
     def barrier():
+        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
@@ -296,6 +326,7 @@ def run_ours(args):
         t0.record()
         for _ in range(n_steps):
             one_block(True, host_io)
+        drain()             # the last collector rounds belong to the timed region
         t1.record()
         barrier()
         ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
@@ -340,6 +371,9 @@ def run_ours(args):
         mon.terminate()
         mon.wait()
     kern = [(a.elapsed_time(b), sw) for a, b, sw in ev_pool]
+    if acol is not None:
+        refit_ms = list(acol.round_ms)
+        acol.round_ms.clear()
     rf = [a.elapsed_time(b) for a, b in refit_ms]
     ev_pool.clear(); refit_ms.clear()
 
@@ -353,6 +387,8 @@ def run_ours(args):
     e2e_steps = max(2, min(args.steps, 8))
     ms_e2e = timed_region(e2e_steps, io)
     ev_pool.clear(); refit_ms.clear()
+    if acol is not None:
+        acol.close()
 
     if rank != 0:
         if world > 1:
@@ -382,8 +418,10 @@ def run_ours(args):
         "config": {"workload": "%s: %s" % (args.workload, w["name"]), "chains_per_gpu": C_, "lockstep_steps_per_bench_step": K,
                    "no_parameters": d, "no_observations": m, "centers": n_c or None,
                    "l2": "256 MiB flush write before every bench step, inside the timed region",
-                   "refit": ("every %d steps: compact + all-gather + thin + dense solve (%s, N=%d) + broadcast; %.2f ms avg inside the step"
-                             % (K, w.get("solver_type", "direct"), n_c + d + 1, float(np.mean(rf)))) if rf else "frozen surrogate"},
+                   "refit": ("every %d steps: compact + all-gather + thin + dense solve (%s, N=%d) + broadcast; %.2f ms avg per round; %s"
+                             % (K, w.get("solver_type", "direct"), n_c + d + 1, float(np.mean(rf)),
+                                "asynchronous collector: round b runs on a side stream during block b+1, its surrogate is used from block b+2"
+                                if overlap else "synchronous between blocks")) if rf else "frozen surrogate"},
         "e2e": {"value": e2e_value, "unit": "chain steps/s", "h2d_bytes_per_step": int(pin_in.numel() * 8),
                 "d2h_bytes_per_step": int(pin_u.numel() * 8 + pin_c.numel() * 4), "steps": e2e_steps,
                 "ms_per_step": ms_e2e / e2e_steps},
@@ -470,6 +508,9 @@ def main():
     ap.add_argument("--solver", default="", choices=["", "direct", "nullspace"], help="dense solver of the RBF refit")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--overlap", action="store_true",
+                    help="asynchronous collector: refit on a side stream with a lag of one block (measured slower on one GPU: "
+                         "the refit's latency-bound kernels starve beside the FP64-bound chain kernel; DESIGN.md section 4.3)")
     ap.add_argument("--profile", type=int, default=0, help="run this many bench steps inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -157,6 +157,9 @@ typedef struct sdb_chain_args {
     /* optional trace: surrogate log posterior of the CURRENT sample as used by step k (the
      * pre_posterior_current_sample the reference writes into its data rows); 0 for MH */
     double *pre_cur;      /* DEVICE [K][C], may be NULL */
+    /* != 0: leave room on every SM for kernels of another stream (the collector's refit running concurrently):
+     * at most one CTA of this kernel per SM; the kernel itself is built for 64 registers per thread */
+    int32_t coresident;
 } sdb_chain_args;
 
 /* ---- library ------------------------------------------------------------------------- */

@@ -145,8 +145,9 @@ class ChainBlock:
 
     # ---- K fused steps -------------------------------------------------------------------------
     def run(self, algorithm, n_steps, proposal, surrogate=None, truth=None, trace=None, streams=None,
-            refresh_pre=False, lanes=0, stream=None):
+            refresh_pre=False, lanes=0, stream=None, coresident=False):
         a = self._args(algorithm, L.PHASE_FUSED, surrogate, truth)
+        a.coresident = int(bool(coresident))
         a.n_steps, a.lanes_per_chain, a.refresh_pre = int(n_steps), lanes, int(bool(refresh_pre))
         a.prop_kind, a.prop_scale = proposal.kind, L.ptr(proposal.scale)
         self._fill_rng(a, streams)

@@ -124,3 +124,79 @@ class Collector:
     def set_model_from_sol(self, SOL):
         """Start from a given surrogate (reference-shaped SOL list)."""
         self.model = self.model_factory(self.surrogate_type, SOL[0], SOL[1])
+
+
+class AsyncCollector:
+    """The collector as a concurrent actor, like the reference's separate COLLECTOR process
+    (process_COLLECTOR.py runs beside the samplers, which keep stepping with the surrogate they have until a
+    new one arrives -- classes_communication.py:137-150).  Here the asynchrony is deterministic: the snapshots
+    of block b are refitted on a side CUDA stream WHILE block b+1 is being stepped, and the new surrogate is
+    switched in at the start of block b+2 (a fixed lag of one block), so a run is reproducible.
+
+    A host thread drives the side stream, because one collector round contains host synchronisations (snapshot
+    counts, solver status); the sampling thread never blocks on them -- it only makes its stream wait on the
+    round's completion event when it needs that round's surrogate.
+    """
+
+    def __init__(self, collector, device, stream=None):
+        import queue
+        import threading
+        self.col = collector
+        self.device = torch.device(device)
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=self.device)
+        self.jobs = queue.Queue()
+        self.results = {}
+        self.cv = threading.Condition()
+        self.error = None
+        self.round_ms = []                    # (start_event, end_event) pairs of the timed rounds
+        self.thread = threading.Thread(target=self._work, daemon=True)
+        self.thread.start()
+
+    def _work(self):
+        from .chains import compact_snapshots
+        torch.cuda.set_device(self.device)
+        while True:
+            job = self.jobs.get()
+            if job is None:
+                return
+            b, trace, K, cap, chain_done, step, timed = job
+            try:
+                with torch.cuda.stream(self.stream):
+                    self.stream.wait_event(chain_done)
+                    r0 = torch.cuda.Event(enable_timing=True)
+                    r1 = torch.cuda.Event(enable_timing=True)
+                    r0.record()
+                    par, obs, cnt = compact_snapshots(trace, K, cap)
+                    did = self.col.exchange_and_refit(par, obs, cnt, step)
+                    r1.record()
+                    if timed:
+                        self.round_ms.append((r0, r1))
+                    res = (r1, self.col.model if did else None)
+            except BaseException as e:      # surfaced in the sampling thread by result()
+                self.error = e
+                res = (None, None)
+            with self.cv:
+                self.results[b] = res
+                self.cv.notify_all()
+
+    def submit(self, b, trace, K, cap, chain_done_event, step, timed=False):
+        self.jobs.put((b, trace, K, cap, chain_done_event, step, timed))
+
+    def result(self, b):
+        """(completion event, new surrogate or None) of round b; waits (host side) until the round has been issued."""
+        with self.cv:
+            while b not in self.results:
+                self.cv.wait(timeout=0.05)
+                if self.error is not None:
+                    raise self.error
+            if self.error is not None:
+                raise self.error
+            return self.results[b]
+
+    def forget(self, b):
+        with self.cv:
+            self.results.pop(b, None)
+
+    def close(self):
+        self.jobs.put(None)
+        self.thread.join(timeout=10)

@@ -55,7 +55,7 @@ __device__ __forceinline__ void eval_model_lane(const sdb_smodel &s, int d, int 
 }
 
 template <int D, int M>
-__global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, const int L) {
+__global__ void __launch_bounds__(512, 2) chain_kernel(const sdb_chain_args a, const int L) {
     constexpr int DD = D ? D : SDB_MAX_D;
     constexpr int UD = D ? D : 1;  // unroll only the specialised sizes
     constexpr int MM = M ? M : SDB_MAX_M;
@@ -425,7 +425,14 @@ static int plan(const sdb_chain_args *a, int *L_out, int *threads_out, int *bloc
     if (threads < 64) threads = 64;
     if (threads > 512) threads = 512;
     const int64_t blocks = (lanes + threads - 1) / threads;
-    *L_out = L; *threads_out = threads; *blocks_out = (int)blocks; *smem_out = (int)smem;
+    size_t smem_req = smem;
+    if (a->coresident) {
+        // more than half of the shared memory per CTA -> at most one CTA of this kernel per SM; the rest of the SM
+        // (registers: 64 per thread here; shared memory: what is left) stays available to other streams
+        const size_t half = (size_t)dp.smem_optin / 2 + 2048;
+        if (smem_req < half) smem_req = half;
+    }
+    *L_out = L; *threads_out = threads; *blocks_out = (int)blocks; *smem_out = (int)smem_req;
     return SDB_OK;
 }
 
