@@ -360,6 +360,14 @@ def run_ours(args):
     p1.record()
     p1.synchronize()
     fp64_peak_tf = pb * 256 * 8 * 2.0 * iters / (p0.elapsed_time(p1) * 1e-3) / 1e12
+    pout.zero_()
+    L.check(L.lib().sdb_fp64_probe3(iters, pb, L.ptr(pout), L.stream_handle()))
+    pout.zero_()
+    p0.record()
+    L.check(L.lib().sdb_fp64_probe3(iters, pb, L.ptr(pout), L.stream_handle()))
+    p1.record()
+    p1.synchronize()
+    fp64_peak3_tf = pb * 256 * 8 * 2.0 * iters / (p0.elapsed_time(p1) * 1e-3) / 1e12
 
     # ---- timed: device-resident --------------------------------------------------------------------------
     L.lib().sdb_launch_count(1)
@@ -433,7 +441,7 @@ def run_ours(args):
                                      "in profiles/r01_chain_kernel_ncu.md; algorithmic bytes = C*K*25 B trace + state = 1.05e8",
                      "kernel": "chain_kernel<%d,%d>" % (d, m),
                      "kernel_ms": avg_ms, "kernel_share_of_step": avg_ms * len(kern) / ms_total,
-                     "flops_per_launch": flops_launch,
+                     "flops_per_launch": flops_launch, "peak_three_register_fma": fp64_peak3_tf,
                      "peak_source": "sdb_fp64_probe (8 independent DFMA chains/thread), measured live in this run; "
                                     "MEASURED_PEAKS.json has no FP64 entry"},
         "clocks": clocks_summary(clk_path, local, wall0, wall1),

@@ -158,7 +158,7 @@ typedef struct sdb_chain_args {
      * pre_posterior_current_sample the reference writes into its data rows); 0 for MH */
     double *pre_cur;      /* DEVICE [K][C], may be NULL */
     /* != 0: leave room on every SM for kernels of another stream (the collector's refit running concurrently):
-     * at most one CTA of this kernel per SM; the kernel itself is built for 64 registers per thread */
+     * at most one CTA of this kernel per SM (its shared-memory request is padded past half of the SM's) */
     int32_t coresident;
 } sdb_chain_args;
 
@@ -249,6 +249,8 @@ SDB_API int64_t sdb_launch_count(int32_t reset);
 /* FP64 FMA throughput probe (roofline denominator of the FP64-pipe-bound kernels):
  * FLOPs = blocks * 256 * 8 * 2 * iters.  d_out: DEVICE doubles [blocks * 256]. */
 SDB_API int sdb_fp64_probe(int64_t iters, int32_t blocks, double *d_out, void *stream);
+/* Same FLOP count, but each FMA reads three distinct live registers (the operand pattern of real code). */
+SDB_API int sdb_fp64_probe3(int64_t iters, int32_t blocks, double *d_out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -93,6 +93,7 @@ _SIGNATURES = {
     "sdb_dgemm": (C.c_int, [_I, _I, _I, C.c_double, _P, _L, _L, _P, _L, _L, C.c_double, _P, _L, _I, _P, _P]),
     "sdb_launch_count": (C.c_int64, [_I]),
     "sdb_fp64_probe": (C.c_int, [_L, _I, _P, _P]),
+    "sdb_fp64_probe3": (C.c_int, [_L, _I, _P, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

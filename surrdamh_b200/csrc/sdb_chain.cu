@@ -55,7 +55,7 @@ __device__ __forceinline__ void eval_model_lane(const sdb_smodel &s, int d, int 
 }
 
 template <int D, int M>
-__global__ void __launch_bounds__(512, 2) chain_kernel(const sdb_chain_args a, const int L) {
+__global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, const int L) {
     constexpr int DD = D ? D : SDB_MAX_D;
     constexpr int UD = D ? D : 1;  // unroll only the specialised sizes
     constexpr int MM = M ? M : SDB_MAX_M;

@@ -153,22 +153,35 @@ __device__ __forceinline__ void sdb_bulk_stage(void *smem_dst, const void *gmem_
 // ---------------------------------------------------------------------------------------
 // small math
 // ---------------------------------------------------------------------------------------
-// 1/sqrt(s) for the pair loops: MUFU.RSQ64H seed (relative error e ~ 2^-22) + ONE third-order
-// correction y (1 + e/2 + 3 e^2/8), e = 1 - s y^2 -- five FP64-pipe operations, error ~ e^3, i.e. the
-// result is rounded-to-nearest quality.  The s == 0 / subnormal guard is an integer test on the high word
-// (ALU pipe, not the FP64 pipe that bounds these loops); it yields 0, so s * rsqrt(s) = 0 without a NaN.
-__device__ __forceinline__ double sdb_fast_rsqrt(double s) {
+// Square roots for the pair loops.  y0 = MUFU.RSQ64H(s) (relative error e ~ 2^-22) and ONE third-order correction:
+//   1/sqrt(s) = y0 (1 + q),  sqrt(s) = t (1 + q),  t = s y0,  q = e/2 + 3 e^2/8,  e = 1 - s y0^2
+// (error ~ e^3: rounded-to-nearest quality).  The callers fold the (1 + q) factor into their last multiply, so
+// r^3 = s^(3/2) costs 6 FP64-pipe operations from s:  t, e, p, q, a = s t, fma(a, q, a).
+// The s == 0 / subnormal guard is an integer test on the high word (ALU pipe, not the FP64 pipe that bounds
+// these loops); it yields y0 = 0, hence t = 0 and every kernel value 0 without a NaN.
+struct sdb_rs {
+    double y0, t, q;
+};
+__device__ __forceinline__ sdb_rs sdb_rsqrt_parts(double s) {
+    sdb_rs o;
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
     const int hi = __double2hiint(s);
-    y = __hiloint2double(hi < 0x00100000 ? 0 : __double2hiint(y), 0);   // RSQ64H fills the high word only
-    const double t = s * y;
-    const double e = fma(-t, y, 1.0);
+    o.y0 = __hiloint2double(hi < 0x00100000 ? 0 : __double2hiint(y), 0);   // RSQ64H fills the high word only
+    o.t = s * o.y0;
+    const double e = fma(-o.t, o.y0, 1.0);
     const double p = fma(0.375, e, 0.5);
-    const double q = e * p;
-    return fma(y, q, y);
+    o.q = e * p;
+    return o;
 }
-__device__ __forceinline__ double sdb_fast_sqrt(double s) { return s * sdb_fast_rsqrt(s); }
+__device__ __forceinline__ double sdb_fast_rsqrt(double s) {
+    const sdb_rs r = sdb_rsqrt_parts(s);
+    return fma(r.y0, r.q, r.y0);
+}
+__device__ __forceinline__ double sdb_fast_sqrt(double s) {
+    const sdb_rs r = sdb_rsqrt_parts(s);
+    return fma(r.t, r.q, r.t);
+}
 
 __device__ __forceinline__ double sdb_shfl_xor(double v, int lanemask, unsigned mask = 0xffffffffu) {
     return __shfl_xor_sync(mask, v, lanemask);
@@ -180,10 +193,10 @@ __device__ __forceinline__ double sdb_shfl(double v, int src, unsigned mask = 0x
 // phi(r) from s = r^2 for the reference's kernel types (surrogate_rbf.py:146-173).
 __device__ __forceinline__ double sdb_rbf_phi(double s, int kernel_type) {
     switch (kernel_type) {
-        case 1: { const double r = sdb_fast_sqrt(s); return s * r; }            // r^3
-        case 2: { const double r = sdb_fast_sqrt(s); return s * s * r; }        // r^5
-        case 3: { const double r = sdb_fast_sqrt(s); return s * s * s * r; }    // r^7
-        case 7: { const double r = sdb_fast_sqrt(s); const double s2 = s * s; return s2 * s2 * r; }  // r^9
+        case 1: { const sdb_rs r = sdb_rsqrt_parts(s); const double a = s * r.t; return fma(a, r.q, a); }            // r^3
+        case 2: { const sdb_rs r = sdb_rsqrt_parts(s); const double a = s * s * r.t; return fma(a, r.q, a); }        // r^5
+        case 3: { const sdb_rs r = sdb_rsqrt_parts(s); const double a = s * s * s * r.t; return fma(a, r.q, a); }    // r^7
+        case 7: { const sdb_rs r = sdb_rsqrt_parts(s); const double s2 = s * s; const double a = s2 * s2 * r.t; return fma(a, r.q, a); }  // r^9
         case 4: return exp(-s);                                                  // exp(-r^2)
         case 5: return sdb_fast_rsqrt(s + 1.0);                                  // (r^2+1)^(-1/2)
         default: return sdb_fast_sqrt(s);                                        // 0 and 6: r

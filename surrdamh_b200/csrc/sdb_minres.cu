@@ -219,6 +219,32 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(int64_t iters, double *
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// Same, but every FMA reads three DIFFERENT live registers per chain (a_k = fma(a_k, b_k, c_k), b_k and c_k loaded from
+// memory), the operand pattern of real FP64 code; tells register-file limits apart from pipe limits.
+__global__ void __launch_bounds__(256) fp64_probe3_kernel(int64_t iters, double *out) {
+    double a[8], b[8], c[8];
+    const size_t base = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        a[k] = 1.0 + k;
+        b[k] = 1.0 + out[base] * 1e-30 + k * 1e-9;      // opaque to the compiler
+        c[k] = 1e-7 + out[base] * 1e-30 + k * 1e-9;
+    }
+    for (int64_t i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = fma(a[k], b[k], c[k]);
+    }
+    out[base] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+}
+
+extern "C" int sdb_fp64_probe3(int64_t iters, int32_t blocks, double *d_out, void *stream) {
+    SDB_CHECK_ARG(iters >= 1 && blocks >= 1 && d_out, "sdb_fp64_probe3: bad arguments");
+    sdb_count_launch();
+    fp64_probe3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, d_out);
+    SDB_CUDA(cudaGetLastError());
+    return SDB_OK;
+}
+
 extern "C" int sdb_fp64_probe(int64_t iters, int32_t blocks, double *d_out, void *stream) {
     SDB_CHECK_ARG(iters >= 1 && blocks >= 1 && d_out, "sdb_fp64_probe: bad arguments");
     sdb_count_launch();
