@@ -239,11 +239,18 @@ static __global__ void __launch_bounds__(256, 2) sdb_gemm_k64_kernel(const doubl
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    // C - A B is accumulated as (-A) B + C: the C tile is loaded into the accumulators NOW, while the cp.async copies
+    // are in flight, so the epilogue is a plain store (no exposed read-modify-write latency at the end)
     double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gm = m0 + wm + i * 8 + gid, gn = n0 + wn + j * 8 + tig * 2 + e;
+                acc[i][j][e] = (!ASSIGN && gm < M && gn < N) ? C[(int64_t)gn * ld + gm] : 0.0;
+            }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         if (half == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -255,7 +262,7 @@ static __global__ void __launch_bounds__(256, 2) sdb_gemm_k64_kernel(const doubl
                 const int k = half * 32 + ks;
                 double fa[4], fb[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) fa[i] = As[k + tig][wm + i * 8 + gid];
+                for (int i = 0; i < 4; ++i) fa[i] = ASSIGN ? As[k + tig][wm + i * 8 + gid] : -As[k + tig][wm + i * 8 + gid];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) fb[j] = BT ? Bt[k + tig][wn + j * 8 + gid] : Bs[wn + j * 8 + gid][k + tig];
 #pragma unroll
@@ -274,8 +281,7 @@ static __global__ void __launch_bounds__(256, 2) sdb_gemm_k64_kernel(const doubl
                 const int gm = m0 + wm + i * 8 + gid, gn = n0 + wn + j * 8 + tig * 2 + e;
                 if (gm < M && gn < N) {
                     double *p = C + (int64_t)gn * ld + gm;
-                    if (ASSIGN) *p = acc[i][j][e];
-                    else *p -= acc[i][j][e];
+                    *p = acc[i][j][e];
                 }
             }
 }
