@@ -433,12 +433,19 @@ __global__ void __launch_bounds__(1024, 1) thin_remove_kernel(const double *__re
         const int v = brow;
         if (v == INT_MAX) break;  // fewer than two alive points
         if (tid == 0) keep[v] = 0;
-        // rows whose nearest neighbour was the victim must be rescanned
-        for (int base = 0; base < n; base += 1024) {
-            const int i = base + tid;
-            if (i < n && i != v && keep[i] && nn_idx[i] == v) todo[atomicAdd(&ntodo, 1)] = i;   // at most 1024 per chunk
+        // rows whose nearest neighbour was the victim must be rescanned (usually one or two rows); collected in one
+        // pass, repeated only if more than 1024 rows pointed at the victim
+        bool again;
+        do {
+            for (int i = tid; i < n; i += blockDim.x)
+                if (i != v && keep[i] && nn_idx[i] == v) {
+                    const int slot = atomicAdd(&ntodo, 1);
+                    if (slot < 1024) todo[slot] = i;
+                }
             __syncthreads();
-            const int cnt = ntodo;
+            const int found = ntodo;
+            again = found > 1024;
+            const int cnt = again ? 1024 : found;
             for (int t = 0; t < cnt; ++t) {   // the whole CTA scans one row at a time
                 const int row = todo[t];
                 double b = DBL_MAX;
@@ -453,8 +460,8 @@ __global__ void __launch_bounds__(1024, 1) thin_remove_kernel(const double *__re
             }
             __syncthreads();
             if (tid == 0) ntodo = 0;
-        }
-        __syncthreads();
+            __syncthreads();
+        } while (again);
     }
     if (use_smem) {
         __syncthreads();
