@@ -444,6 +444,12 @@ def run_ours(args):
                      "flops_per_launch": flops_launch, "peak_three_register_fma": fp64_peak3_tf,
                      "peak_source": "sdb_fp64_probe (8 independent DFMA chains/thread), measured live in this run; "
                                     "MEASURED_PEAKS.json has no FP64 entry"},
+        "roofline_hbm": {"bound": "hbm", "frac": (float(C_) * K * (25 if w["updated"] else 0) + 2.0 * C_ * (8 * (d + m + 2) + 16))
+                         / (avg_ms * 1e-3) / 1e9 / 6548.2, "achieved": (float(C_) * K * (25 if w["updated"] else 0) + 2.0 * C_ * (8 * (d + m + 2) + 16))
+                         / (avg_ms * 1e-3) / 1e9, "peak": 6548.2, "unit": "GB/s",
+                         "note": "the same kernel against the measured HBM copy bandwidth of MEASURED_PEAKS.json: algorithmic bytes "
+                                 "(flags + snapshot trace, state read + written once per launch) over the launch time -- far from "
+                                 "the HBM roofline, which is why the FP64 pipe is the bound reported above"},
         "clocks": clocks_summary(clk_path, local, wall0, wall1),
     }
     if cpu is not None:

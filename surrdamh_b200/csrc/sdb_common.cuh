@@ -165,11 +165,7 @@ struct sdb_rs {
 __device__ __forceinline__ sdb_rs sdb_rsqrt_parts(double s) {
     sdb_rs o;
     double y;
-#ifdef SDB_EXP_NOMUFU   // timing experiment only (wrong values): integer seed instead of MUFU.RSQ64H
-    y = __hiloint2double(0x5fe6eb50 - (__double2hiint(s) >> 1), 0);
-#else
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
-#endif
     const int hi = __double2hiint(s);
     o.y0 = __hiloint2double(hi < 0x00100000 ? 0 : __double2hiint(y), 0);   // RSQ64H fills the high word only
     o.t = s * o.y0;
