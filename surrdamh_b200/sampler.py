@@ -150,8 +150,12 @@ class LockstepSampler:
                 if col.exchange_and_refit(par, obs, cnt, self.global_step, timed=timed_refit):
                     if kind == "DAMH":
                         surrogate, swapped = col.model, True
-            if time.time() - t0 > time_limit:
-                break
+            if time_limit != float("inf"):
+                # the limit is wall time of finished work (classes_SAMPLER.py:156,215 checks it every step): wait for this
+                # block, otherwise the host would queue blocks far past the limit
+                torch.cuda.current_stream(self.device).synchronize()
+                if time.time() - t0 > time_limit:
+                    break
         torch.cuda.synchronize(self.device)
         if hasattr(self.trace_sink, "end_stage"):
             self.trace_sink.end_stage(i, st, self, done)

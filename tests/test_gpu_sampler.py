@@ -168,3 +168,66 @@ def test_csv_traces_match_reference_files(tmp_path):
                 acc = [r for r in csv.reader(open(base / "DAMH_accepted" / (name + ".csv")))]
                 rej = [r for r in csv.reader(open(base / "DAMH_rejected" / (name + ".csv")))]
                 assert len(acc) == g[f"st{i}_c{c}_counters"][0] and len(rej) == g[f"st{i}_c{c}_counters"][1]
+
+
+def test_stage_options_initial_sample_proposal_differs_time_limit_and_errors():
+    """process_SAMPLER.py:53-64 stage keys: per-stage `initial_sample`, `proposal_differs` (per-chain proposal_std indexed by
+    the global chain), `time_limit`; a DAMH stage before any surrogate fails like the reference (TypeError on SOL = None)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from surrdamh_b200.sampler import LockstepSampler
+    C_ = 8
+    stds = [0.1 * (c + 1) for c in range(C_)]
+    conf = _conf({"samplers_list": [
+        {"type": "MH", "max_samples": 30, "time_limit": 60, "proposal_std": stds, "proposal_differs": True, "surrogate_is_updated": True,
+         "initial_sample": [6.5, 3.5]},
+        {"type": "DAMH", "max_samples": 10 ** 9, "time_limit": 0.3, "proposal_std": 0.5, "surrogate_is_updated": False}],
+        "initial_sample_type": "prior_mean", "refit_every": 10, "seed": 4})
+    seen = {}
+
+    def sink(stage, step0, K, tr):
+        if stage == 0 and step0 == 0:
+            seen["prop0"] = tr.prop[0].cpu().numpy().copy()
+    smp = LockstepSampler(conf, no_chains=C_, trace_sink=sink)
+    z, _ = smp.block.philox_streams(1, step0=0)
+    r0 = smp.run_stage(0, conf.list_alg[0])
+    # first proposal of chain c = initial_sample + std_c * z_c   (stage sub-stream 0 == the block's default stream id)
+    zn = z.cpu().numpy()[0]
+    want = np.array([6.5, 3.5])[:, None] + np.array(stds)[None, :] * zn
+    assert np.array_equal(seen["prop0"], want)
+    assert r0.steps == 30 and r0.refits == 3
+    r1 = smp.run_stage(1, conf.list_alg[1])                      # stops on the time limit, between blocks
+    assert 0 < r1.steps < 10 ** 9 and r1.seconds < 5.0
+    assert int(r1.counters[:, :3].sum()) == r1.steps * C_
+    conf2 = _conf({"samplers_list": [{"type": "DAMH", "max_samples": 5, "time_limit": 60, "proposal_std": 0.5,
+                                      "surrogate_is_updated": True}], "initial_sample_type": "prior_mean"})
+    with pytest.raises(TypeError):
+        LockstepSampler(conf2, no_chains=4).run()
+
+
+def test_minres_initial_iteration_and_iteration_limit():
+    """surr_updater_parameters of the reference's RBF updater: `initial_iteration` (x0 of MINRES) and the iteration limit
+    (scipy's info = maxiter when it is hit)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import scipy.sparse.linalg as splin
+    from oracle import surrogate_rbf as ORB
+    from surrdamh_b200 import surrogate_rbf as SR
+    rs = np.random.RandomState(31)
+    X, Y = rs.standard_normal((150, 3)), rs.standard_normal((150, 1))
+    ref = ORB.RbfUpdate(3, 1, kernel_type=1, solver_type="direct")
+    ref.add_arrays(X, Y)
+    (COd, _), _ = ref.update()
+    S, b = ref.last_system, ref.last_rhs[:, 0]
+    x0 = COd[:, 0] * (1 + 1e-3 * rs.standard_normal(COd.shape[0]))       # a good starting point: few iterations
+    up = SR.Surrogate_update(3, 1, kernel_type=1, solver_type="minres", initial_iteration=x0)
+    up.add_arrays(X, Y)
+    (CO, _), _ = up.update()
+    want, info_ref = splin.minres(S, b, x0=x0, rtol=1e-6)
+    assert up.last_info[0] == info_ref == 0
+    assert np.linalg.norm(CO[:, 0] - want) <= 1e-2 * np.linalg.norm(want)
+    assert np.linalg.norm(S @ CO[:, 0] - b) <= 2.0 * np.linalg.norm(S @ want - b) + 1e-12
+    up2 = SR.Surrogate_update(3, 1, kernel_type=1, solver_type="minres", max_iterations=7)
+    up2.add_arrays(X, Y)
+    up2.update()
+    assert up2.last_info[0] == 7 and up2.last_info[1] == 7 and up2.last_info[2] == 6     # scipy: info = maxiter, istop = 6
