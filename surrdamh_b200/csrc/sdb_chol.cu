@@ -194,32 +194,34 @@ __global__ void __launch_bounds__(256, 1) chol_potrf64_kernel(double *__restrict
 
 // X = L11^{-1} (64 x 64 lower triangular) -> Xout column-major with leading dimension 64.  Four lanes share a
 // column: row i of X needs sum_k L(i, k) X(k, c), split over the lanes and combined with two shuffles; only those
-// four lanes ever read column c, so a warp-level sync per row suffices.  The panel's triangular solve then
+// sixteen lanes ever read column c, so a warp-level sync per row suffices.  The panel's triangular solve then
 // becomes one DMMA multiplication L21 = A21 X^T (sdb_gemm_k64_inplace).
-__global__ void __launch_bounds__(256, 1) chol_trinv64_kernel(const double *__restrict__ A, int64_t ld, int k0, int h,
-                                                              double *__restrict__ Xout) {
+__global__ void __launch_bounds__(1024, 1) chol_trinv64_kernel(const double *__restrict__ A, int64_t ld, int k0, int h,
+                                                               double *__restrict__ Xout) {
     // one 64 x 65 array holds both triangles: L(i, c) at Ls[i][c] (c <= i), X(k, c) at Ls[c][k + 1] (k >= c)
     __shared__ double Ls[64][65];
     __shared__ double rdiag[64];
     const int tid = threadIdx.x;
-    for (int e = tid; e < 64 * 64; e += 256) {
+    for (int e = tid; e < 64 * 64; e += 1024) {
         const int i = e & 63, c = e >> 6;
         if (c <= i) Ls[i][c] = (i < h) ? A[(int64_t)(k0 + c) * ld + k0 + i] : (i == c ? 1.0 : 0.0);
     }
     __syncthreads();
     if (tid < 64) rdiag[tid] = 1.0 / Ls[tid][tid];
     __syncthreads();
-    const int c = tid >> 2, part = tid & 3;
+    const int c = tid >> 4, part = tid & 15;     // sixteen lanes share a column: at most 4 terms of the row sum each
     for (int i = 0; i < 64; ++i) {      // uniform trip count: the full-mask shuffles need every lane of the warp
         double s = 0.0;
-        for (int k = c + part; k < i; k += 4) s = fma(Ls[i][k], Ls[c][k + 1], s);
+        for (int k = c + part; k < i; k += 16) s = fma(Ls[i][k], Ls[c][k + 1], s);
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
         if (part == 0 && i >= c) Ls[c][i + 1] = ((i == c ? 1.0 : 0.0) - s) * rdiag[i];
         __syncwarp();
     }
     __syncthreads();
-    for (int e = tid; e < 64 * 64; e += 256) {
+    for (int e = tid; e < 64 * 64; e += 1024) {
         const int i = e & 63, cc = e >> 6;
         Xout[cc * 64 + i] = (i < h && cc < h && cc <= i) ? Ls[cc][i + 1] : 0.0;
     }
@@ -271,25 +273,36 @@ __global__ void __launch_bounds__(256) chol_trsv_block_kernel(const double *__re
 __global__ void __launch_bounds__(256) chol_fwd_kernel(const double *__restrict__ A, int64_t ld, const double *__restrict__ Linv,
                                                        double *__restrict__ B, double *__restrict__ X, int64_t ldb, int k0, int h,
                                                        int nb, int m) {
+    __shared__ double Ls[64][65];      // Ls[t][k] = Linv(t, k): staged with coalesced, independent loads
     __shared__ double bb[64], xs[64];
     const int t = threadIdx.x;
+    for (int e = t; e < 64 * 64; e += 256) Ls[e & 63][e >> 6] = Linv[e];      // Linv[k*64 + t]
     for (int rhs = 0; rhs < m; ++rhs) {
         double *b = B + (int64_t)rhs * ldb;
         if (t < 64) bb[t] = t < h ? b[k0 + t] : 0.0;
         __syncthreads();
-        if (t < 64) {
+        {
+            const int o = t >> 2, part = t & 3;               // four lanes per entry of the block solution
             double s = 0.0;
-            for (int k = 0; k <= t && k < h; ++k) s = fma(Linv[k * 64 + t], bb[k], s);
-            xs[t] = t < h ? s : 0.0;
-            if (blockIdx.x == 0 && t < h) X[(int64_t)rhs * ldb + k0 + t] = s;
+            for (int k = part; k <= o && k < h; k += 4) s = fma(Ls[o][k], bb[k], s);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (part == 0) {
+                xs[o] = o < h ? s : 0.0;
+                if (blockIdx.x == 0 && o < h) X[(int64_t)rhs * ldb + k0 + o] = s;
+            }
         }
         __syncthreads();
         const int r = k0 + h + blockIdx.x * 256 + t;
         if (r < nb) {
-            double acc = 0.0;
+            double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll 8
-            for (int k = 0; k < h; ++k) acc = fma(A[(int64_t)(k0 + k) * ld + r], xs[k], acc);
-            b[r] -= acc;
+            for (int k = 0; k + 1 < h; k += 2) {
+                acc0 = fma(A[(int64_t)(k0 + k) * ld + r], xs[k], acc0);
+                acc1 = fma(A[(int64_t)(k0 + k + 1) * ld + r], xs[k + 1], acc1);
+            }
+            if (h & 1) acc0 = fma(A[(int64_t)(k0 + h - 1) * ld + r], xs[h - 1], acc0);
+            b[r] -= acc0 + acc1;
         }
         __syncthreads();
     }
@@ -298,26 +311,37 @@ __global__ void __launch_bounds__(256) chol_fwd_kernel(const double *__restrict_
 __global__ void __launch_bounds__(256) chol_bwd_kernel(const double *__restrict__ A, int64_t ld, const double *__restrict__ Linv,
                                                        double *__restrict__ W, double *__restrict__ Y, int64_t ldb, int k0, int h,
                                                        int m) {
+    __shared__ double Ls[64][65];      // Ls[k][t] = Linv(k, t), read as Linv^T(t, k)
     __shared__ double wb[64], ys[64];
     const int t = threadIdx.x;
+    for (int e = t; e < 64 * 64; e += 256) Ls[e & 63][e >> 6] = Linv[e];      // Linv[c*64 + i] -> Ls[i][c]
     for (int rhs = 0; rhs < m; ++rhs) {
         double *w = W + (int64_t)rhs * ldb;
         if (t < 64) wb[t] = t < h ? w[k0 + t] : 0.0;
         __syncthreads();
-        if (t < 64) {
+        {
+            const int o = t >> 2, part = t & 3;
             double s = 0.0;
-            for (int k = t; k < h; ++k) s = fma(Linv[t * 64 + k], wb[k], s);      // Linv^T(t, k) = Linv(k, t)
-            ys[t] = t < h ? s : 0.0;
-            if (blockIdx.x == 0 && t < h) Y[(int64_t)rhs * ldb + k0 + t] = s;
+            for (int k = o + part; k < h; k += 4) s = fma(Ls[k][o], wb[k], s);   // Linv^T(o, k) = Linv(k, o)
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (part == 0) {
+                ys[o] = o < h ? s : 0.0;
+                if (blockIdx.x == 0 && o < h) Y[(int64_t)rhs * ldb + k0 + o] = s;
+            }
         }
         __syncthreads();
         const int i = blockIdx.x * 256 + t;
         if (i < k0) {
             const double *a = A + (int64_t)i * ld + k0;        // L(k0 + k, i), contiguous in k
-            double acc = 0.0;
+            double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll 8
-            for (int k = 0; k < h; ++k) acc = fma(a[k], ys[k], acc);
-            w[i] -= acc;
+            for (int k = 0; k + 1 < h; k += 2) {
+                acc0 = fma(a[k], ys[k], acc0);
+                acc1 = fma(a[k + 1], ys[k + 1], acc1);
+            }
+            if (h & 1) acc0 = fma(a[h - 1], ys[h - 1], acc0);
+            w[i] -= acc0 + acc1;
         }
         __syncthreads();
     }
@@ -423,7 +447,7 @@ static int ns_enqueue(cudaStream_t st, double *S, int n, int d, int m, int kerne
         const int rest = nb - k0 - h;
         double *xinv = xinv_all + (int64_t)(k0 / 64) * 4096;
         sdb_count_launch();
-        chol_trinv64_kernel<<<1, 256, 0, st>>>(A, ld, k0, h, xinv);
+        chol_trinv64_kernel<<<1, 1024, 0, st>>>(A, ld, k0, h, xinv);
         if (rest > 0) {
             double *L21 = A + (int64_t)k0 * ld + k0 + h;
             // L21 = A21 L11^{-T}:  (A21 X^T)(r, j) = sum_k A21(r, k) X(j, k),  X(j, k) = xinv[k*64 + j]
