@@ -108,6 +108,9 @@ __global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, c
     const bool writer = active && sub == 0;
     const uint64_t gchain = (uint64_t)(a.chain0 + c);
     const bool damh = a.algorithm == SDB_ALG_DAMH;
+    // speculative evaluation of a cheap analytic truth: only in fused launches too small to fill the GPU
+    const bool spec_truth = a.phase == SDB_PHASE_FUSED && (tru.kind == SDB_MODEL_TOY || tru.kind == SDB_MODEL_ZERO) &&
+                            (int64_t)gridDim.x * blockDim.x <= 148 * 256;
 
     double u[DD], Gu[MM];
 #pragma unroll UD
@@ -165,6 +168,8 @@ __global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, c
         }
         if (a.pre_cur && writer && a.phase != SDB_PHASE_DECIDE) a.pre_cur[row] = pre_u;
         bool pass1;
+        double lp_p = 0.0, post_p_spec = 0.0;
+        bool have_lp = false;
         if (a.phase != SDB_PHASE_DECIDE) {
             // ---- proposal: u' = u + sigma*z, separately rounded (numpy: loc + scale*gauss) -------
             double z[DD];
@@ -197,10 +202,19 @@ __global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, c
             }
             // ---- stage 1: surrogate posterior of the proposal (:185-193) --------------------------
             pass1 = true;
+            lp_p = sdb_log_prior<D, M>(pr, up);       // shared by the surrogate and the true posterior of this proposal
+            have_lp = true;
+            if (spec_truth) {
+                // latency-bound launches (few chains): the cheap analytic truth is evaluated for every proposal, off
+                // the critical path of the stage-1 test; same arithmetic, same result, the value is simply unused
+                // after a pre-rejection
+                eval_model_lane<D, M>(tru, d, m, up, Gp, 0, 1);
+                post_p_spec = __dadd_rn(sdb_log_likelihood<D, M>(pr, Gp), lp_p);
+            }
             if (damh) {
                 double S[MM];
                 eval_model_lane<D, M>(sur, d, m, up, S, sub, L);
-                pre_p = sdb_log_posterior<D, M>(pr, up, S);
+                pre_p = __dadd_rn(sdb_log_likelihood<D, M>(pr, S), lp_p);
                 pass1 = log(uni0) < __dadd_rn(pre_p, -pre_u);
             }
             if (a.phase == SDB_PHASE_PROPOSE) {
@@ -231,12 +245,13 @@ __global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, c
             }
         } else if (tru.kind == SDB_MODEL_RBF) {
             sdb_rbf_point_warp<D, M>(tru, d, m, up, Gp, pass1 && active, L);
-        } else if (pass1) {
+        } else if (pass1 && !spec_truth) {
             eval_model_lane<D, M>(tru, d, m, up, Gp, 0, 1);
         }
         int flag = SDB_FLAG_PREREJECTED;
         if (pass1) {
-            post_p = sdb_log_posterior<D, M>(pr, up, Gp);
+            if (spec_truth) post_p = post_p_spec;
+            else post_p = __dadd_rn(sdb_log_likelihood<D, M>(pr, Gp), have_lp ? lp_p : sdb_log_prior<D, M>(pr, up));
             const double log_ratio = __dadd_rn(post_p, -post_u);
             bool acc;
             if (damh) acc = log(uni1) < __dadd_rn(log_ratio, -__dadd_rn(pre_p, -pre_u));  // stage 2 (:195)

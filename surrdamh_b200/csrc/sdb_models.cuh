@@ -295,43 +295,44 @@ __device__ __forceinline__ double sdb_quad_lu(const double *lu, const int *piv, 
     return -0.5 * q;
 }
 
+// log-likelihood and log-prior separately: the prior of a proposal is needed twice per DAMH step (surrogate and
+// true posterior, classes_SAMPLER.py:189-191,79-80) and is computed once; ll + lp is rounded exactly as the
+// reference's get_log_likelihood(G) + get_log_prior(u).
 template <int D, int M>
-__device__ __forceinline__ double sdb_log_posterior(const sdb_sproblem &p, const double *u, const double *G) {
-    constexpr int DD = D ? D : SDB_MAX_D;
-    constexpr int UD = D ? D : 1;  // unroll only the specialised sizes
+__device__ __forceinline__ double sdb_log_likelihood(const sdb_sproblem &p, const double *G) {
     constexpr int MM = M ? M : SDB_MAX_M;
     constexpr int UM = M ? M : 1;
-    const int d = D ? D : p.d, m = M ? M : p.m;
-    double ll, lp;
-    {
-        double v[MM];
+    const int m = M ? M : p.m;
+    double v[MM];
 #pragma unroll UM
-        for (int k = 0; k < MM; ++k)
-            if (k < m) v[k] = __dadd_rn(p.obs[k], -G[k]);
-        if (p.noise_full) {
-            ll = sdb_quad_lu<MM>(p.noise_scale, p.noise_piv, m, v);
-        } else {
-            double q = 0.0;
+    for (int k = 0; k < MM; ++k)
+        if (k < m) v[k] = __dadd_rn(p.obs[k], -G[k]);
+    if (p.noise_full) return sdb_quad_lu<MM>(p.noise_scale, p.noise_piv, m, v);
+    double q = 0.0;
 #pragma unroll UM
-            for (int k = 0; k < MM; ++k)
-                if (k < m) q = __dadd_rn(q, __dmul_rn(v[k], __ddiv_rn(v[k], p.noise_scale[k])));
-            ll = -0.5 * q;
-        }
-    }
-    {
-        double v[DD];
+    for (int k = 0; k < MM; ++k)
+        if (k < m) q = __dadd_rn(q, __dmul_rn(v[k], __ddiv_rn(v[k], p.noise_scale[k])));
+    return -0.5 * q;
+}
+
+template <int D, int M>
+__device__ __forceinline__ double sdb_log_prior(const sdb_sproblem &p, const double *u) {
+    constexpr int DD = D ? D : SDB_MAX_D;
+    constexpr int UD = D ? D : 1;  // unroll only the specialised sizes
+    const int d = D ? D : p.d;
+    double v[DD];
 #pragma unroll UD
-        for (int j = 0; j < DD; ++j)
-            if (j < d) v[j] = __dadd_rn(u[j], -p.prior_mean[j]);
-        if (p.prior_full) {
-            lp = sdb_quad_lu<DD>(p.prior_scale, p.prior_piv, d, v);
-        } else {
-            double q = 0.0;
+    for (int j = 0; j < DD; ++j)
+        if (j < d) v[j] = __dadd_rn(u[j], -p.prior_mean[j]);
+    if (p.prior_full) return sdb_quad_lu<DD>(p.prior_scale, p.prior_piv, d, v);
+    double q = 0.0;
 #pragma unroll UD
-            for (int j = 0; j < DD; ++j)
-                if (j < d) q = __dadd_rn(q, __dmul_rn(v[j], __ddiv_rn(v[j], p.prior_scale[j])));
-            lp = -0.5 * q;
-        }
-    }
-    return __dadd_rn(ll, lp);
+    for (int j = 0; j < DD; ++j)
+        if (j < d) q = __dadd_rn(q, __dmul_rn(v[j], __ddiv_rn(v[j], p.prior_scale[j])));
+    return -0.5 * q;
+}
+
+template <int D, int M>
+__device__ __forceinline__ double sdb_log_posterior(const sdb_sproblem &p, const double *u, const double *G) {
+    return __dadd_rn(sdb_log_likelihood<D, M>(p, G), sdb_log_prior<D, M>(p, u));
 }
