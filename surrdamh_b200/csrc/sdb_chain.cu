@@ -10,6 +10,7 @@
 //
 // Follows classes_SAMPLER.py:54-101,122-128,147-220 (see include/surrdamh_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "sdb_models.cuh"
 
@@ -346,6 +347,231 @@ __global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, c
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Lean fused kernel for the reference's own toy shape (simple.json / BASELINE configs[0..1]): d = 2, m = 1, polynomial
+// surrogate of degree <= 6 (or plain MH), analytic toy / zero truth, one thread per chain.  Few chains cannot fill
+// the GPU, so a step is bound by the LATENCY of its dependent chain; this kernel shortens that chain:
+//   * the random numbers of step k+1 (Philox, Box-Muller, both log-uniforms) do not depend on the chain state and
+//     are computed during step k (software pipelining),
+//   * the Hermite-Vandermonde evaluation is fully unrolled with the tables in registers / broadcast shared memory
+//     (terms in nested-loop order; the coefficient column is permuted once per CTA to match),
+//   * the cheap truth and the prior are evaluated for every proposal, next to the surrogate, not after its test.
+// Same arithmetic per quantity as chain_kernel (same device functions for the likelihood, prior and toy model),
+// so decisions and trace values are identical; only the order of the PHI.MAT accumulation differs (as BLAS's does).
+// ---------------------------------------------------------------------------------------------------------------
+struct lean_rng {
+    double z0, z1, lu0, lu1;
+};
+
+__device__ __forceinline__ lean_rng lean_draw(const sdb_chain_args &a, uint64_t gchain, int64_t c, int64_t C, int k) {
+    lean_rng r;
+    double u0, u1;
+    if (a.rng_kind == SDB_RNG_STREAMS) {
+        r.z0 = a.z[((size_t)k * 2 + 0) * C + c];
+        r.z1 = a.z[((size_t)k * 2 + 1) * C + c];
+        u0 = a.uni[((size_t)k * 2 + 0) * C + c];
+        u1 = a.uni[((size_t)k * 2 + 1) * C + c];
+    } else {
+        const uint64_t gstep = (uint64_t)(a.step0 + k);
+        sdb_normal_pair(sdb_chain_block(a.seed, a.stream_id, gchain, gstep, 0u), r.z0, r.z1);
+        const philox4 b = sdb_chain_block(a.seed, a.stream_id, gchain, gstep, SDB_SLOT_UNIFORMS);
+        u0 = sdb_u01(b.x, b.y);
+        u1 = sdb_u01(b.z, b.w);
+    }
+    r.lu0 = log(u0);
+    r.lu1 = log(u1);
+    return r;
+}
+
+template <int DEG, bool DAMH>
+__global__ void __launch_bounds__(128) chain_lean_kernel(const sdb_chain_args a) {
+    constexpr int NH = DEG + 1;
+    constexpr int P = (DEG + 1) * (DEG + 2) / 2;
+    const int64_t C = a.state.n_chains;
+    __shared__ __align__(16) unsigned char lsm[1024];
+    __shared__ double herm[NH * NH];
+    __shared__ double matc[P];          // MAT in nested-loop order (a0 outer, a1 inner)
+    unsigned char *p = lsm;
+    sdb_sproblem pr;
+    pr.d = 2; pr.m = 1; pr.prior_full = a.problem.prior_full; pr.noise_full = 0;
+    {
+        size_t b;
+        b = 16; pr.prior_mean = (const double *)p; copy_small(p, a.problem.prior_mean, b); p += 16;
+        b = (size_t)(pr.prior_full ? 4 : 2) * 8; pr.prior_scale = (const double *)p; copy_small(p, a.problem.prior_scale, b); p += 32;
+        pr.prior_piv = (const int *)p; copy_small(p, a.problem.prior_piv, 8); p += 16;
+        pr.obs = (const double *)p; copy_small(p, a.problem.obs, 8); p += 16;
+        pr.noise_scale = (const double *)p; copy_small(p, a.problem.noise_scale, 8); p += 16;
+        pr.noise_piv = nullptr;
+    }
+    const double *prop_shared = (const double *)p;
+    if (a.prop_kind == SDB_PROP_SHARED) copy_small(p, a.prop_scale, 16);
+    if (DAMH) {
+        for (int e = threadIdx.x; e < NH * NH; e += blockDim.x) herm[e] = a.surrogate.herm[e];
+        if (threadIdx.x < P) {           // canonical index -> (a0, a1) -> row of the reference's multi-index table
+            int t = threadIdx.x, a0 = 0;
+            while (t > DEG - a0) { t -= DEG - a0 + 1; ++a0; }
+            const int a1 = t;
+            double v = 0.0;
+            for (int row = 0; row < a.surrogate.n_terms; ++row)
+                if (a.surrogate.alpha[row * 2] == a0 && a.surrogate.alpha[row * 2 + 1] == a1) v = a.surrogate.coefs[row];
+            matc[threadIdx.x] = v;
+        }
+    }
+    __syncthreads();
+    sdb_smodel tru;
+    tru.kind = a.truth.kind; tru.toy_f = a.truth.toy_f; tru.toy_L = a.truth.toy_L; tru.toy_M = a.truth.toy_M;
+
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const uint64_t gchain = (uint64_t)(a.chain0 + c);
+    double u0 = a.state.u[c], u1 = a.state.u[C + c], Gu = a.state.G_u[c];
+    double post_u = a.state.post_u[c], pre_u = a.state.pre_u[c];
+    int n_acc = a.state.counters[0 * C + c], n_rej = a.state.counters[1 * C + c];
+    int n_pre = a.state.counters[2 * C + c], rej_cur = a.state.counters[3 * C + c];
+    const bool do_mom = a.state.moments != nullptr;
+    double mom[5] = {0, 0, 0, 0, 0};
+    if (do_mom)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) mom[i] = a.state.moments[(size_t)i * C + c];
+    const double sig0 = a.prop_kind == SDB_PROP_PER_CHAIN ? a.prop_scale[c] : prop_shared[0];
+    const double sig1 = a.prop_kind == SDB_PROP_PER_CHAIN ? a.prop_scale[C + c] : prop_shared[1];
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    auto surrogate_post = [&](const double *x, double lp) -> double {
+        // normalised-Hermite Vandermonde x MAT, the reference's per-value operation order (surrogate_poly.py:162-175,26-29)
+        double h0[NH], h1[NH];
+        {
+            double pw[NH];
+            pw[0] = 1.0;
+#pragma unroll
+            for (int i = 1; i <= DEG; ++i) pw[i] = __dmul_rn(pw[i - 1], x[0]);
+#pragma unroll
+            for (int k = 0; k <= DEG; ++k) {
+                double v = herm[k * NH];
+#pragma unroll
+                for (int i = 1; i <= k; ++i) v = __dadd_rn(v, __dmul_rn(herm[k * NH + i], pw[i]));
+                h0[k] = v;
+            }
+            pw[0] = 1.0;
+#pragma unroll
+            for (int i = 1; i <= DEG; ++i) pw[i] = __dmul_rn(pw[i - 1], x[1]);
+#pragma unroll
+            for (int k = 0; k <= DEG; ++k) {
+                double v = herm[k * NH];
+#pragma unroll
+                for (int i = 1; i <= k; ++i) v = __dadd_rn(v, __dmul_rn(herm[k * NH + i], pw[i]));
+                h1[k] = v;
+            }
+        }
+        double Sp[3] = {0.0, 0.0, 0.0};     // three interleaved partial sums: a third of the dependent FMA chain
+        int t = 0;
+#pragma unroll
+        for (int a0 = 0; a0 <= DEG; ++a0)
+#pragma unroll
+            for (int a1 = 0; a1 <= DEG - a0; ++a1) {
+                Sp[t % 3] = fma(__dmul_rn(h0[a0], h1[a1]), matc[t], Sp[t % 3]);
+                ++t;
+            }
+        const double S = (Sp[0] + Sp[1]) + Sp[2];
+        return __dadd_rn(sdb_log_likelihood<2, 1>(pr, &S), lp);
+    };
+
+    if (DAMH && a.refresh_pre) {
+        const double x[2] = {u0, u1};
+        pre_u = surrogate_post(x, sdb_log_prior<2, 1>(pr, x));
+    }
+
+    const int K = a.n_steps;
+    lean_rng nxt = lean_draw(a, gchain, c, C, 0);
+    for (int k = 0; k < K; ++k) {
+        const lean_rng cur = nxt;
+        if (k + 1 < K) nxt = lean_draw(a, gchain, c, C, k + 1);   // independent of the chain state: overlaps this step
+        const size_t row = (size_t)k * C + c;
+        if (a.pre_cur) a.pre_cur[row] = pre_u;
+        double up[2];
+        up[0] = __dadd_rn(u0, __dmul_rn(sig0, cur.z0));
+        up[1] = __dadd_rn(u1, __dmul_rn(sig1, cur.z1));
+        const double lp_p = sdb_log_prior<2, 1>(pr, up);
+        double Gp = 0.0;
+        if (tru.kind == SDB_MODEL_TOY) Gp = sdb_toy_G(tru, up);
+        const double post_p = __dadd_rn(sdb_log_likelihood<2, 1>(pr, &Gp), lp_p);
+        double pre_p = qnan;
+        bool pass1 = true;
+        if (DAMH) {
+            pre_p = surrogate_post(up, lp_p);
+            pass1 = cur.lu0 < __dadd_rn(pre_p, -pre_u);
+        }
+        const double log_ratio = __dadd_rn(post_p, -post_u);
+        const bool acc = pass1 && (DAMH ? (cur.lu1 < __dadd_rn(log_ratio, -__dadd_rn(pre_p, -pre_u))) : (cur.lu0 < log_ratio));
+        const int flag = !pass1 ? SDB_FLAG_PREREJECTED : (acc ? SDB_FLAG_ACCEPTED : SDB_FLAG_REJECTED);
+        if (a.flags) a.flags[row] = (uint8_t)flag;
+        if (a.prop) {
+            a.prop[((size_t)k * 2 + 0) * C + c] = up[0];
+            a.prop[((size_t)k * 2 + 1) * C + c] = up[1];
+        }
+        if (a.post) a.post[row] = pass1 ? post_p : qnan;
+        if (a.pre) a.pre[row] = pre_p;
+        if (a.snap_par && pass1) {       // displaced current sample on accept, the proposal on reject (:85,:98)
+            a.snap_par[((size_t)k * 2 + 0) * C + c] = acc ? u0 : up[0];
+            a.snap_par[((size_t)k * 2 + 1) * C + c] = acc ? u1 : up[1];
+            a.snap_obs[row] = acc ? Gu : Gp;
+        }
+        n_acc += acc;
+        n_rej += (pass1 && !acc);
+        n_pre += !pass1;
+        rej_cur = acc ? 0 : rej_cur + 1;
+        u0 = acc ? up[0] : u0;
+        u1 = acc ? up[1] : u1;
+        Gu = acc ? Gp : Gu;
+        post_u = acc ? post_p : post_u;
+        if (DAMH) pre_u = acc ? pre_p : pre_u;
+        if (do_mom) {
+            mom[0] += u0; mom[1] += u1;
+            mom[2] = fma(u0, u0, mom[2]); mom[3] = fma(u0, u1, mom[3]); mom[4] = fma(u1, u1, mom[4]);
+        }
+    }
+    a.state.u[c] = u0; a.state.u[C + c] = u1; a.state.G_u[c] = Gu;
+    a.state.post_u[c] = post_u; a.state.pre_u[c] = pre_u;
+    a.state.counters[0 * C + c] = n_acc; a.state.counters[1 * C + c] = n_rej;
+    a.state.counters[2 * C + c] = n_pre; a.state.counters[3 * C + c] = rej_cur;
+    if (do_mom)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) a.state.moments[(size_t)i * C + c] = mom[i];
+}
+
+static bool lean_applicable(const sdb_chain_args *a) {
+    if (getenv("SDB_NO_LEAN")) return false;
+    if (a->phase != SDB_PHASE_FUSED || a->problem.d != 2 || a->problem.m != 1 || a->problem.noise_full) return false;
+    if (a->lanes_per_chain > 1 || a->coresident) return false;
+    if (a->prop_kind != SDB_PROP_SHARED && a->prop_kind != SDB_PROP_PER_CHAIN) return false;
+    if (a->truth.kind != SDB_MODEL_TOY && a->truth.kind != SDB_MODEL_ZERO) return false;
+    if (a->algorithm == SDB_ALG_DAMH)
+        return a->surrogate.kind == SDB_MODEL_POLY && a->surrogate.degree >= 1 && a->surrogate.degree <= 6;
+    return true;
+}
+
+template <int DEG>
+static void lean_launch_deg(const sdb_chain_args *a, int blocks, cudaStream_t st) {
+    if (a->algorithm == SDB_ALG_DAMH) chain_lean_kernel<DEG, true><<<blocks, 128, 0, st>>>(*a);
+    else chain_lean_kernel<1, false><<<blocks, 128, 0, st>>>(*a);
+}
+
+static int lean_launch(const sdb_chain_args *a, cudaStream_t st) {
+    const int64_t C = a->state.n_chains;
+    const int blocks = (int)((C + 127) / 128);
+    sdb_count_launch();
+    switch (a->algorithm == SDB_ALG_DAMH ? a->surrogate.degree : 1) {
+        case 1: lean_launch_deg<1>(a, blocks, st); break;
+        case 2: lean_launch_deg<2>(a, blocks, st); break;
+        case 3: lean_launch_deg<3>(a, blocks, st); break;
+        case 4: lean_launch_deg<4>(a, blocks, st); break;
+        case 5: lean_launch_deg<5>(a, blocks, st); break;
+        default: lean_launch_deg<6>(a, blocks, st); break;
+    }
+    SDB_CUDA(cudaGetLastError());
+    return SDB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
@@ -461,6 +687,7 @@ extern "C" int sdb_chain_plan(const sdb_chain_args *args, int *lanes_per_chain, 
 extern "C" int sdb_chain_run(const sdb_chain_args *args, void *stream) {
     int rc = validate(args);
     if (rc) return rc;
+    if (lean_applicable(args)) return lean_launch(args, (cudaStream_t)stream);
     int L, threads, blocks, smem;
     rc = plan(args, &L, &threads, &blocks, &smem);
     if (rc) return rc;

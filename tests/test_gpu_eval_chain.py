@@ -157,9 +157,14 @@ def _check_against_golden(G, tr, blk, g, prefix, c, init, check_rows=True):
         assert close(rows[:, -1], want[:, rows.shape[1] - 1], rtol=RTOL)          # posterior of the current sample
 
 
-@pytest.mark.parametrize("split", [False, True])
-def test_mh_and_damh_poly_golden(G, split):
+@pytest.mark.parametrize("split", [False, True, "generic"])
+def test_mh_and_damh_poly_golden(G, split, monkeypatch):
+    """split False: fused launch (the lean d = 2 kernel); "generic": the same through the generic fused kernel
+    (SDB_NO_LEAN); True: PROPOSE / DECIDE phases with the host evaluating G."""
     from surrdamh_b200.device import DeviceModel
+    if split == "generic":
+        monkeypatch.setenv("SDB_NO_LEAN", "1")
+        split = False
     g = load("chains")
     C_, K = [int(x) for x in g["chains_meta"]]
     sur = DeviceModel.poly(g["poly_MAT"], int(g["poly_deg"]), 2)
