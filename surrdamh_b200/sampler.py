@@ -62,6 +62,11 @@ class LockstepSampler:
         self.truth = None
         if conf.device_solver and hasattr(self.solver, "device_model"):
             self.truth = self.solver.device_model()
+        # host-evaluated G with no_solvers > 1: a pool of solver processes, as the reference's process_SOLVER / process_CHILD
+        self.pool = None
+        if self.truth is None and solver is None and getattr(conf, "no_full_solvers", 1) > 1 and "solver_module_path" in conf.conf:
+            from .solver_pool import HostSolverPool
+            self.pool = HostSolverPool.from_conf(conf)
         self.trace_sink, self.streams = trace_sink, streams
         self.chain0 = rank * self.C                               # global index of this rank's first chain
         self.block = ChainBlock(self.problem, self.C, initial=self._initial_samples(), chain0=self.chain0, seed=conf.seed,
@@ -98,6 +103,10 @@ class LockstepSampler:
         return Proposal(self.d, st["proposal_std"], device=self.device)
 
     def _host_G(self, params):
+        if self.pool is not None:
+            out = self.pool.evaluate(params)
+            self.no_G_calls_host += params.shape[0]
+            return out.reshape(params.shape[0], self.m)
         out = np.empty((params.shape[0], self.m))
         for i, p in enumerate(params):
             self.solver.set_parameters(p)

@@ -154,3 +154,24 @@ def test_shipped_example_configs_load():
                 assert st["type"] in ("MH", "DAMH") and "proposal_std" in st and "surrogate_is_updated" in st
     finally:
         os.chdir(cwd)
+
+
+def test_host_solver_pool_matches_sequential_plugin_calls():
+    """no_solvers > 1 with a host-evaluated G: the pool of solver processes (process_SOLVER / process_CHILD) returns,
+    in order, exactly what one solver instance called sequentially returns."""
+    from surrdamh_b200.solver_pool import HostSolverPool
+    from surrdamh_b200.solvers import Solver_linela2exp_local
+    rs = np.random.RandomState(3)
+    P = rs.standard_normal((37, 2)) + np.array([5.0, 3.0])
+    pool = HostSolverPool(3, os.path.join(ROOT, "surrdamh_b200", "solvers.py"), "solvers", "Solver_linela2exp_local", {})
+    try:
+        got = pool.evaluate(P)
+        assert pool.evaluate(P[:1]).shape == (1, 1) and pool.no_calls == 38
+    finally:
+        pool.close()
+    s = Solver_linela2exp_local()
+    want = []
+    for p in P:
+        s.set_parameters(p)
+        want.append([s.get_observations()])
+    assert np.array_equal(got, np.array(want))

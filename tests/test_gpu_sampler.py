@@ -43,7 +43,7 @@ def _streams_for(N, conf, device):
     return streams
 
 
-@pytest.mark.parametrize("device_solver", [True, False])
+@pytest.mark.parametrize("device_solver", [True, False, "pool"])
 def test_simple_json_lockstep_bit_identical_to_reference(device_solver):
     """simple.json, 4 chains, refit every 50 steps.  Chains, proposal / uniform streams and the refit
     schedule are those of the golden run; the surrogate coefficients installed at each refit are the
@@ -55,7 +55,10 @@ def test_simple_json_lockstep_bit_identical_to_reference(device_solver):
     from surrdamh_b200.sampler import LockstepSampler
     g = load("simple_lockstep")
     N, R, total = [int(x) for x in g["meta"]]
-    conf = _conf({"refit_every": R, "device_solver": device_solver})
+    use_pool = device_solver == "pool"       # no_solvers = 2: the host G goes through the pool of solver processes
+    if use_pool:
+        device_solver = False
+    conf = _conf({"refit_every": R, "device_solver": device_solver, "no_solvers": 2 if use_pool else 1})
     flags = {}
 
     def sink(stage, step0, K, tr):
@@ -81,6 +84,9 @@ def test_simple_json_lockstep_bit_identical_to_reference(device_solver):
                 assert np.array_equal(smp.block.current_numpy()[c], g[f"st{i}_c{c}_final"])
     if not device_solver:
         assert smp.no_G_calls_host > 0
+    assert (smp.pool is not None) == use_pool
+    if smp.pool is not None:
+        smp.pool.close()
 
 
 def test_full_gpu_pipeline_matches_oracle_in_distribution():
