@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(256) ns_syr2_kernel(double *__restrict__ Phi, 
 // Cholesky (lower, column-major, leading dimension ld) of the nb x nb matrix A, 64-column blocks
 // ---------------------------------------------------------------------------------------------------
 // 64 x 64 diagonal block in ONE CTA of 256 threads arranged 16 x 16; thread (ty, tx) keeps the 4 x 4 tile
-// rows 4ty.., columns 4tx.. in registers.  Per column: the diagonal owner publishes sqrt(a_jj), the owners of
-// column j publish the scaled column, everybody applies the rank-1 update to its tile: two barriers per column.
+// rows 4ty.., columns 4tx.. in registers.  Per column: the owners of column j publish it unscaled (double-buffered),
+// every thread forms 1/sqrt(a_jj) itself and applies the rank-1 update to its tile: ONE barrier per column.
 __global__ void __launch_bounds__(256, 1) chol_potrf64_kernel(double *__restrict__ A, int64_t ld, int k0, int h, int *__restrict__ info) {
     __shared__ double col[2][64];     // the UNSCALED column j, double-buffered: one barrier per column
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(256, 1) chol_potrf64_kernel(double *__restrict
         }
 }
 
-// X = L11^{-1} (64 x 64 lower triangular) -> Xout column-major with leading dimension 64.  Four lanes share a
-// column: row i of X needs sum_k L(i, k) X(k, c), split over the lanes and combined with two shuffles; only those
+// X = L11^{-1} (64 x 64 lower triangular) -> Xout column-major with leading dimension 64.  Sixteen lanes share a
+// column: row i of X needs sum_k L(i, k) X(k, c), split over the lanes and combined with four shuffles; only those
 // sixteen lanes ever read column c, so a warp-level sync per row suffices.  The panel's triangular solve then
 // becomes one DMMA multiplication L21 = A21 X^T (sdb_gemm_k64_inplace).
 __global__ void __launch_bounds__(1024, 1) chol_trinv64_kernel(const double *__restrict__ A, int64_t ld, int k0, int h,
@@ -224,42 +224,6 @@ __global__ void __launch_bounds__(1024, 1) chol_trinv64_kernel(const double *__r
     for (int e = tid; e < 64 * 64; e += 1024) {
         const int i = e & 63, cc = e >> 6;
         Xout[cc * 64 + i] = (i < h && cc < h && cc <= i) ? Ls[cc][i + 1] : 0.0;
-    }
-}
-
-// one warp per right-hand side: x = L11^{-1} b (TRANS = false) or L11^{-T} b (TRANS = true) on a block of h <= 64 rows
-template <bool TRANS>
-__global__ void __launch_bounds__(256) chol_trsv_block_kernel(const double *__restrict__ A, int64_t ld, double *__restrict__ B,
-                                                              int64_t ldb, int k0, int h, int nrhs) {
-    __shared__ double T[64][65];   // T[i][k] = L(k0+i, k0+k), k <= i
-    for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
-        const int i = e & 63, k = e >> 6;
-        T[i][k] = (i < h && k <= i) ? A[(int64_t)(k0 + k) * ld + k0 + i] : (i == k ? 1.0 : 0.0);
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    for (int rhs = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rhs < nrhs; rhs += gridDim.x * (blockDim.x >> 5)) {
-        double *b = B + (int64_t)rhs * ldb + k0;
-        double x0 = lane < h ? b[lane] : 0.0, x1 = lane + 32 < h ? b[lane + 32] : 0.0;
-        if (!TRANS) {
-            for (int i = 0; i < h; ++i) {
-                double xi = __shfl_sync(0xffffffffu, i < 32 ? x0 : x1, i & 31);
-                xi = xi / T[i][i];
-                if (lane == (i & 31)) { if (i < 32) x0 = xi; else x1 = xi; }
-                if (lane > i) x0 = fma(-T[lane][i], xi, x0);
-                if (lane + 32 > i) x1 = fma(-T[lane + 32][i], xi, x1);
-            }
-        } else {
-            for (int i = h - 1; i >= 0; --i) {
-                double xi = __shfl_sync(0xffffffffu, i < 32 ? x0 : x1, i & 31);
-                xi = xi / T[i][i];
-                if (lane == (i & 31)) { if (i < 32) x0 = xi; else x1 = xi; }
-                if (lane < i) x0 = fma(-T[i][lane], xi, x0);            // L^T(lane, i) = L(i, lane)
-                if (lane + 32 < i) x1 = fma(-T[i][lane + 32], xi, x1);
-            }
-        }
-        if (lane < h) b[lane] = x0;
-        if (lane + 32 < h) b[lane + 32] = x1;
     }
 }
 

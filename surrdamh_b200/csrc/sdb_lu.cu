@@ -22,7 +22,6 @@
 namespace cg = cooperative_groups;
 
 #define LU_T 512   // threads per CTA of the base case
-#define LU_W 8     // base-case width
 #define LU_NB 64   // outer panel width
 
 // ---------------------------------------------------------------------------------------------------
