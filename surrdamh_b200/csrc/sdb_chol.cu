@@ -132,190 +132,261 @@ __global__ void __launch_bounds__(256) ns_syr2_kernel(double *__restrict__ Phi, 
 // ---------------------------------------------------------------------------------------------------
 // Cholesky (lower, column-major, leading dimension ld) of the nb x nb matrix A, 64-column blocks
 // ---------------------------------------------------------------------------------------------------
-// 64 x 64 diagonal block in ONE CTA of 256 threads arranged 16 x 16; thread (ty, tx) keeps the 4 x 4 tile
-// rows 4ty.., columns 4tx.. in registers.  Per column: the owners of column j publish it unscaled (double-buffered),
-// every thread forms 1/sqrt(a_jj) itself and applies the rank-1 update to its tile: ONE barrier per column.
-__global__ void __launch_bounds__(256, 1) chol_potrf64_kernel(double *__restrict__ A, int64_t ld, int k0, int h, int *__restrict__ info) {
-    __shared__ double col[2][64];     // the UNSCALED column j, double-buffered: one barrier per column
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    double a[4][4];
+// POTRF + inverse of the 64 x 64 diagonal block, blocked by FOUR columns: the trailing matrix and the growing
+// inverse live in DMMA accumulator fragments (8 x 8 blocks, lower block triangle: every warp owns one block row of A
+// and the complementary block row of X), one warp factors the 64 x 4 panel with shuffles only (no block barrier inside the
+// panel), and the rank-4 updates  A -= Lp Lp^T,  X -= Lp Xr  are m8n8k4 DMMAs whose operands are two small
+// k-major panels in shared memory.  Two block barriers per FOUR columns; shared-memory traffic per column is a
+// few hundred bytes instead of the 8 KB a register-tiled rank-1 update reads back.
+// upd != 0: the block first receives the previous panel's contribution  D -= T T^T,  T = A[k0.., k0-64..k0-1]
+// (the rows of the previous panel solve that face this block), also as DMMAs -- the look-ahead update of the
+// diagonal block is done HERE, so the factorisation's critical path never waits for the panel-wide update kernel.
+// ---------------------------------------------------------------------------------------------------
+#define PI_S 68      // row stride of the k-major panels: == 4 (mod 16) doubles -> conflict-free fragment loads
+#define PI_XS 65     // column stride of the staged inverse: row-wise stores by 32 lanes hit 32 distinct banks
+
+#ifndef SDB_PI_PROF_ARG
+#define SDB_PI_PROF_ARG
+#define SDB_PI_PROF_PASS
+#define SDB_PI_PROF_INIT
+#define SDB_PI_STAMP(i)
+#define SDB_PI_PROF_END
+#endif
+__global__ void __launch_bounds__(256, 1) chol_potrf_inv64_kernel(double *__restrict__ A, int64_t ld, int k0, int h,
+                                                                  double *__restrict__ Xout, int *__restrict__ info, int upd SDB_PI_PROF_ARG) {
+    SDB_PI_PROF_INIT
+    __shared__ __align__(16) double sm[(64 + 16) * PI_S];
+    double (*T)[PI_S] = (double (*)[PI_S])sm;              // prologue: T[k][i]; afterwards the staged inverse Xs[c*PI_XS + i]
+    double *Xs = sm;
+    double (*Lp)[PI_S] = T + 64;                            // final L(:, j0..j0+3), k-major
+    double (*Xr)[PI_S] = Lp + 4;                            // final X(j0..j0+3, :)
+    double (*Pn)[PI_S] = Xr + 4;                            // the panel as extracted from the accumulators (not yet factored)
+    double (*Xn)[PI_S] = Pn + 4;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    // block rows: warps w and w + 4 share a scheduler, so their rows pair up as (0,7) (1,6) (2,5) (3,4)
+    const int ra = w < 4 ? w : 11 - w, bx = 7 - ra;
+    double ca[8][2], cx[8][2];
+    if (upd) {
+        double tv[16];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int i = ty * 4 + r, cc = tx * 4 + c;
-            a[r][c] = (i < h && cc <= i) ? A[(int64_t)(k0 + cc) * ld + k0 + i] : (i == cc ? 1.0 : 0.0);
+        for (int u = 0; u < 16; ++u) {                      // all sixteen loads in flight before the first store
+            const int e = tid + u * 256, i = e & 63, c = e >> 6;
+            tv[u] = i < h ? A[(int64_t)(k0 - 64 + c) * ld + k0 + i] : 0.0;
         }
-    for (int jb = 0; jb < 16; ++jb) {            // column block; inside, the 4 columns are unrolled (static register indices)
 #pragma unroll
-        for (int jc = 0; jc < 4; ++jc) {
-            const int j = jb * 4 + jc;
-            if (j < h) {                          // uniform
-                double *cj = col[j & 1];
-                if (tx == jb) {
+        for (int u = 0; u < 16; ++u) {
+            const int e = tid + u * 256;
+            T[e >> 6][e & 63] = tv[u];
+        }
+    }
+    for (int e = tid; e < 4 * PI_S; e += 256) (&Xn[0][0])[e] = 0.0;      // columns right of the diagonal block are never written
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) cj[ty * 4 + r] = (ty * 4 + r >= j) ? a[r][jc] : 0.0;
+    for (int bj = 0; bj < 8; ++bj)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int i = ra * 8 + gid, c = bj * 8 + tig * 2 + e;
+            ca[bj][e] = (bj <= ra) ? ((i < h && c < h) ? A[(int64_t)(k0 + c) * ld + k0 + i] : (i == c ? 1.0 : 0.0)) : 0.0;
+            cx[bj][e] = (bx * 8 + gid == c) ? 1.0 : 0.0;
+        }
+    __syncthreads();
+    if (upd) {
+#pragma unroll 2
+        for (int kk = 0; kk < 64; kk += 4) {
+            const double fa = -T[kk + tig][ra * 8 + gid];
+#pragma unroll
+            for (int bj = 0; bj < 8; ++bj)
+                if (bj <= ra) sdb_dmma(ca[bj][0], ca[bj][1], fa, T[kk + tig][bj * 8 + gid]);
+        }
+        __syncthreads();                                    // T is reused for the staged inverse below
+    }
+    SDB_PI_STAMP(0)
+    for (int j0 = 0; j0 < h; j0 += 4) {
+        const int bjs = j0 >> 3, hi4 = (j0 >> 2) & 1;      // block column / row of the panel, and which half of the block
+        // (1) the panel's four columns of A and four rows of X leave the accumulators
+        if (ra >= bjs && (tig >> 1) == hi4) {
+#pragma unroll
+            for (int bj = 0; bj < 8; ++bj)
+                if (bj == bjs) {
+                    Pn[(tig & 1) * 2 + 0][ra * 8 + gid] = ca[bj][0];
+                    Pn[(tig & 1) * 2 + 1][ra * 8 + gid] = ca[bj][1];
                 }
-                __syncthreads();
-                const double djj = cj[j];
-                const bool pd = djj > 0.0;
-                if (!pd && tid == 0 && *info == 0) *info = k0 + j + 1;      // not positive definite (or NaN)
-                const double rd = pd ? sdb_fast_rsqrt(djj) : 1.0;           // 1 / L(j, j)
-                if (tx == jb) {
+        }
+        if (bx == bjs && (gid >> 2) == hi4) {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const int i = ty * 4 + r;
-                        a[r][jc] = i > j ? a[r][jc] * rd : (i == j ? (pd ? djj * rd : 1.0) : 0.0);
+            for (int bj = 0; bj < 8; ++bj)
+                if (bj <= bx) {
+                    Xn[gid & 3][bj * 8 + tig * 2 + 0] = cx[bj][0];
+                    Xn[gid & 3][bj * 8 + tig * 2 + 1] = cx[bj][1];
+                }
+        }
+        SDB_PI_STAMP(1)
+        __syncthreads();
+        SDB_PI_STAMP(2)
+        // (2) one warp factors the panel: lane l holds rows l, l + 32 of the panel and columns l, l + 32 of the X rows.
+        // Every lane factors the 4 x 4 pivot block redundantly in registers (broadcast loads, no shuffles): the only
+        // serial chain is four reciprocal square roots.  No masks: rows above the pivot and columns right of it only
+        // ever feed entries that are already final.
+        if (w == 0) {
+            double p[4][2], xq[4][2], g[4][4], rd[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) { p[k][e] = Pn[k][lane + 32 * e]; xq[k][e] = Xn[k][lane + 32 * e]; }
+#pragma unroll
+                for (int i = k; i < 4; ++i) g[i][k] = Pn[k][j0 + i];
+            }
+            int bad = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double d = g[k][k];
+                const bool pd = d > 0.0;
+                if (!pd && !bad) bad = j0 + k + 1;
+                const double rs = sdb_fast_rsqrt(pd ? d : 1.0);
+                rd[k] = pd ? rs : 1.0;                                      // 1 / L(j, j)
+#pragma unroll
+                for (int i = k + 1; i < 4; ++i) g[i][k] *= rd[k];           // L(j0 + i, j0 + k)
+#pragma unroll
+                for (int k2 = k + 1; k2 < 4; ++k2)
+#pragma unroll
+                    for (int i = k2; i < 4; ++i) g[i][k2] = fma(-g[i][k], g[k2][k], g[i][k2]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                double lk[2], xk[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) { lk[e] = p[k][e] * rd[k]; xk[e] = xq[k][e] * rd[k]; }   // row j itself: d * rd = L(j, j)
+#pragma unroll
+                for (int k2 = k + 1; k2 < 4; ++k2)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        p[k2][e] = fma(-lk[e], g[k2][k], p[k2][e]);
+                        xq[k2][e] = fma(-g[k2][k], xk[e], xq[k2][e]);
                     }
-                }
-                if (tx >= jb) {
-                    double lr[4], lc[4];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) lr[r] = cj[ty * 4 + r] * rd;
+                for (int e = 0; e < 2; ++e) { Lp[k][lane + 32 * e] = lk[e]; Xr[k][lane + 32 * e] = xk[e]; }
+            }
+            if (bad && lane == 0 && *info == 0) *info = k0 + bad;           // not positive definite (or NaN)
+        }
+        SDB_PI_STAMP(3)
+        __syncthreads();
+        {   // the factored panel goes out: L to global memory, the X rows to the staging area (one entry per thread each)
+            const int k = tid >> 6, r = tid & 63, j = j0 + k;
+            if (r >= j && r < h) A[(int64_t)(k0 + j) * ld + k0 + r] = Lp[k][r];
+            Xs[r * PI_XS + j] = r <= j ? Xr[k][r] : 0.0;
+        }
+        // (3) rank-4 updates of what is still live: rows / columns beyond the panel of A, rows beyond it of X
+        if (j0 + 4 < h) {
+            const int bj_lo = (j0 + 4) >> 3, bj_hi = (j0 + 3) >> 3;
+            if (ra >= bj_lo) {
+                const double fa = -Lp[tig][ra * 8 + gid];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) lc[c] = cj[tx * 4 + c] * rd;
+                for (int bj = 0; bj < 8; ++bj)
+                    if (bj >= bj_lo && bj <= ra) sdb_dmma(ca[bj][0], ca[bj][1], fa, Lp[tig][bj * 8 + gid]);
+            }
+            if (bx >= bj_lo) {
+                const double fa = -Lp[tig][bx * 8 + gid];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (tx * 4 + c > j) a[r][c] = fma(-lr[r], lc[c], a[r][c]);
-                }
+                for (int bj = 0; bj < 8; ++bj)
+                    if (bj <= bj_hi && bj <= bx) sdb_dmma(cx[bj][0], cx[bj][1], fa, Xr[tig][bj * 8 + gid]);
             }
         }
+        SDB_PI_STAMP(4)
     }
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int i = ty * 4 + r, cc = tx * 4 + c;
-            if (i < h && cc <= i) A[(int64_t)(k0 + cc) * ld + k0 + i] = a[r][c];
-        }
-}
-
-// X = L11^{-1} (64 x 64 lower triangular) -> Xout column-major with leading dimension 64.  Sixteen lanes share a
-// column: row i of X needs sum_k L(i, k) X(k, c), split over the lanes and combined with four shuffles; only those
-// sixteen lanes ever read column c, so a warp-level sync per row suffices.  The panel's triangular solve then
-// becomes one DMMA multiplication L21 = A21 X^T (sdb_gemm_k64_inplace).
-__global__ void __launch_bounds__(1024, 1) chol_trinv64_kernel(const double *__restrict__ A, int64_t ld, int k0, int h,
-                                                               double *__restrict__ Xout) {
-    // one 64 x 65 array holds both triangles: L(i, c) at Ls[i][c] (c <= i), X(k, c) at Ls[c][k + 1] (k >= c)
-    __shared__ double Ls[64][65];
-    __shared__ double rdiag[64];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < 64 * 64; e += 1024) {
+    SDB_PI_PROF_END
+    __syncthreads();
+    for (int e = tid; e < 64 * 64; e += 256) {
         const int i = e & 63, c = e >> 6;
-        if (c <= i) Ls[i][c] = (i < h) ? A[(int64_t)(k0 + c) * ld + k0 + i] : (i == c ? 1.0 : 0.0);
-    }
-    __syncthreads();
-    if (tid < 64) rdiag[tid] = 1.0 / Ls[tid][tid];
-    __syncthreads();
-    const int c = tid >> 4, part = tid & 15;     // sixteen lanes share a column: at most 4 terms of the row sum each
-    for (int i = 0; i < 64; ++i) {      // uniform trip count: the full-mask shuffles need every lane of the warp
-        double s = 0.0;
-        for (int k = c + part; k < i; k += 16) s = fma(Ls[i][k], Ls[c][k + 1], s);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        if (part == 0 && i >= c) Ls[c][i + 1] = ((i == c ? 1.0 : 0.0) - s) * rdiag[i];
-        __syncwarp();
-    }
-    __syncthreads();
-    for (int e = tid; e < 64 * 64; e += 1024) {
-        const int i = e & 63, cc = e >> 6;
-        Xout[cc * 64 + i] = (i < h && cc < h && cc <= i) ? Ls[cc][i + 1] : 0.0;
+        Xout[e] = (i < h && c <= i) ? Xs[c * PI_XS + i] : 0.0;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Triangular solves with the inverses of the diagonal blocks (kept from the factorisation), one kernel per
-// 64-block and direction: every CTA forms the block's solution redundantly (a 64 x 64 mat-vec) and then
-// updates its own rows of the remaining right-hand side.
-//   forward : x_blk = Linv_k b_blk              -> X;   B[r] -= sum_k L(r, k0+k) x_k   for r >= k0 + h
-//   backward: y_blk = Linv_k^T w_blk            -> Y;   W[i] -= sum_k L(k0+k, i) y_k   for i <  k0
+// The whole backward solve  L^T x = y  in ONE cooperative kernel.  CTA g owns the 64-blocks nblk-1-g, nblk-1-g-G, ...
+// (descending); for its block kb it accumulates  s = sum_{jb > kb} L(jb, kb)^T x_jb  as the x_jb are published by
+// their owners (release / acquire flags in global memory, L tiles requested before the wait), then
+// x_kb = Linv_kb^T (y_kb - s).  The critical path per block is one flag hand-over, a 64 x 64 tile product and a
+// 64 x 64 mat-vec instead of a kernel launch.  All CTAs are co-resident (cooperative launch) and every CTA takes its
+// blocks in dependency order, so the waits cannot deadlock.  y: row nb + rhs of A (left there by the factorisation).
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) chol_fwd_kernel(const double *__restrict__ A, int64_t ld, const double *__restrict__ Linv,
-                                                       double *__restrict__ B, double *__restrict__ X, int64_t ldb, int k0, int h,
-                                                       int nb, int m) {
-    __shared__ double Ls[64][65];      // Ls[t][k] = Linv(t, k): staged with coalesced, independent loads
-    __shared__ double bb[64], xs[64];
-    const int t = threadIdx.x;
-    for (int e = t; e < 64 * 64; e += 256) Ls[e & 63][e >> 6] = Linv[e];      // Linv[k*64 + t]
-    for (int rhs = 0; rhs < m; ++rhs) {
-        double *b = B + (int64_t)rhs * ldb;
-        if (t < 64) bb[t] = t < h ? b[k0 + t] : 0.0;
-        __syncthreads();
-        {
-            const int o = t >> 2, part = t & 3;               // four lanes per entry of the block solution
-            double s = 0.0;
-            for (int k = part; k <= o && k < h; k += 4) s = fma(Ls[o][k], bb[k], s);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (part == 0) {
-                xs[o] = o < h ? s : 0.0;
-                if (blockIdx.x == 0 && o < h) X[(int64_t)rhs * ldb + k0 + o] = s;
+__device__ __forceinline__ int ns_ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ns_st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256) chol_bwd_flags_kernel(const double *__restrict__ A, int64_t ld,
+                                                             const double *__restrict__ LinvAll, double *Xv, int64_t ldb, int nb,
+                                                             int m, int *ready) {
+    __shared__ double Ls[64][65];      // Ls[k][o] = Linv(k, o)
+    __shared__ double sv[64], vv[64];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int nblk = (nb + 63) / 64;
+    for (int p = blockIdx.x; p < nblk; p += gridDim.x) {
+        const int kb = nblk - 1 - p, k0 = kb * 64;
+        const int h = (nb - k0) < 64 ? (nb - k0) : 64;
+        const double *Linv = LinvAll + (int64_t)kb * 4096;
+        for (int e = t; e < 64 * 64; e += 256) Ls[e & 63][e >> 6] = Linv[e];      // Linv[c*64 + i] -> Ls[i][c]
+        const int c0 = warp * 8;                                                   // this warp's 8 columns of the block
+        for (int rhs = 0; rhs < m; ++rhs) {
+            double *xg = Xv + (int64_t)rhs * ldb;
+            double acc[8];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) acc[cc] = 0.0;
+            for (int jb = nblk - 1; jb > kb; --jb) {
+                const int r0 = jb * 64 + lane, r1 = r0 + 32;
+                const bool ok0 = r0 < nb, ok1 = r1 < nb;
+                double l0[8], l1[8];
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    const bool okc = c0 + cc < h;
+                    const double *colp = A + (int64_t)(k0 + c0 + cc) * ld;
+                    l0[cc] = (ok0 && okc) ? colp[r0] : 0.0;
+                    l1[cc] = (ok1 && okc) ? colp[r1] : 0.0;
+                }
+                if (lane == 0)
+                    while (ns_ld_acquire(ready + jb) <= rhs) { }
+                __syncwarp();
+                const double x0 = ok0 ? __ldcg(xg + r0) : 0.0, x1 = ok1 ? __ldcg(xg + r1) : 0.0;
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) acc[cc] = fma(l0[cc], x0, fma(l1[cc], x1, acc[cc]));
             }
-        }
-        __syncthreads();
-        const int r = k0 + h + blockIdx.x * 256 + t;
-        if (r < nb) {
-            double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 8
-            for (int k = 0; k + 1 < h; k += 2) {
-                acc0 = fma(A[(int64_t)(k0 + k) * ld + r], xs[k], acc0);
-                acc1 = fma(A[(int64_t)(k0 + k + 1) * ld + r], xs[k + 1], acc1);
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc)
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) acc[cc] += __shfl_xor_sync(0xffffffffu, acc[cc], off);
+            if (lane == 0) {
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) sv[c0 + cc] = acc[cc];
             }
-            if (h & 1) acc0 = fma(A[(int64_t)(k0 + h - 1) * ld + r], xs[h - 1], acc0);
-            b[r] -= acc0 + acc1;
+            __syncthreads();
+            if (t < 64) vv[t] = t < h ? A[(int64_t)(k0 + t) * ld + nb + rhs] - sv[t] : 0.0;
+            __syncthreads();
+            {
+                const int o = t >> 2, part = t & 3;               // four lanes per entry of the block solution
+                double s = 0.0;
+                for (int k = o + part; k < h; k += 4) s = fma(Ls[k][o], vv[k], s);   // Linv^T(o, k) = Linv(k, o)
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                if (part == 0 && o < h) { xg[k0 + o] = s; __threadfence(); }
+            }
+            __syncthreads();
+            if (t == 0) ns_st_release(ready + kb, rhs + 1);
         }
         __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(256) chol_bwd_kernel(const double *__restrict__ A, int64_t ld, const double *__restrict__ Linv,
-                                                       double *__restrict__ W, double *__restrict__ Y, int64_t ldb, int k0, int h,
-                                                       int m) {
-    __shared__ double Ls[64][65];      // Ls[k][t] = Linv(k, t), read as Linv^T(t, k)
-    __shared__ double wb[64], ys[64];
-    const int t = threadIdx.x;
-    for (int e = t; e < 64 * 64; e += 256) Ls[e & 63][e >> 6] = Linv[e];      // Linv[c*64 + i] -> Ls[i][c]
-    for (int rhs = 0; rhs < m; ++rhs) {
-        double *w = W + (int64_t)rhs * ldb;
-        if (t < 64) wb[t] = t < h ? w[k0 + t] : 0.0;
-        __syncthreads();
-        {
-            const int o = t >> 2, part = t & 3;
-            double s = 0.0;
-            for (int k = o + part; k < h; k += 4) s = fma(Ls[k][o], wb[k], s);   // Linv^T(o, k) = Linv(k, o)
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (part == 0) {
-                ys[o] = o < h ? s : 0.0;
-                if (blockIdx.x == 0 && o < h) Y[(int64_t)rhs * ldb + k0 + o] = s;
-            }
-        }
-        __syncthreads();
-        const int i = blockIdx.x * 256 + t;
-        if (i < k0) {
-            const double *a = A + (int64_t)i * ld + k0;        // L(k0 + k, i), contiguous in k
-            double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 8
-            for (int k = 0; k + 1 < h; k += 2) {
-                acc0 = fma(a[k], ys[k], acc0);
-                acc1 = fma(a[k + 1], ys[k + 1], acc1);
-            }
-            if (h & 1) acc0 = fma(a[h - 1], ys[h - 1], acc0);
-            w[i] -= acc0 + acc1;
-        }
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(256) ns_scale_rhs_kernel(double *__restrict__ F, int64_t ldf, int q, int n, int m, double scale) {
-    const int64_t total = (int64_t)(n - q) * m;
+// right-hand sides (m columns of F, rows q..n-1, after Q^T) -> m extra ROWS below B22, times the definiteness sign:
+// the factorisation's panel solve and trailing update then carry out the forward substitution on them for free
+__global__ void __launch_bounds__(256) ns_rhs_rows_kernel(const double *__restrict__ F, int64_t ldf, double *__restrict__ A, int64_t ld,
+                                                          int q, int nb, int m, double scale) {
+    const int64_t total = (int64_t)nb * m;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int k = (int)(e / (n - q)), i = q + (int)(e % (n - q));
-        F[(int64_t)k * ldf + i] *= scale;
+        const int k = (int)(e / nb), c = (int)(e % nb);
+        A[(int64_t)c * ld + nb + k] = scale * F[(int64_t)k * ldf + q + c];
     }
 }
 
@@ -366,16 +437,19 @@ __global__ void __launch_bounds__(NS_T, 1) ns_finish_kernel(const double *__rest
 
 static bool ns_kernel_supported(int kt) { return kt == 0 || kt == 1 || kt == 4 || kt == 5 || kt == 6; }
 
-static int ns_enqueue(cudaStream_t st, double *S, int n, int d, int m, int kernel_type, double *F, double *COEFS,
+// leading dimension of the system in the work buffer: room for the m right-hand-side rows below row n
+static inline int64_t ns_ld(int64_t n, int d, int m) { return n + (m > d + 1 ? m : d + 1); }
+
+static int ns_enqueue(cudaStream_t st, double *S, int64_t ld, int n, int d, int m, int kernel_type, double *F, double *COEFS,
                       double *vec, int32_t *d_info) {
-    const int q = d + 1, N = n + q, nb = n - q;
-    const int64_t ld = N;
+    const int q = d + 1, nb = n - q;
     double *P = S + (int64_t)n * ld;
     double *tau = vec, *v = vec + 64, *w = v + n, *z = w + n;
-    double *xf = z + n;                                   // forward-solve result, m columns of length ld
-    double *xinv_all = xf + (int64_t)m * ld;              // inverse of every 64 x 64 diagonal block
+    double *xinv_all = z + n;                              // inverse of every 64 x 64 diagonal block
+    int *ready = (int *)(xinv_all + (int64_t)(nb / 64 + 1) * 4096);
     const double sgn = (kernel_type == 0 || kernel_type == 6) ? -1.0 : 1.0;
     SDB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
+    SDB_CUDA(cudaMemsetAsync(ready, 0, sizeof(int) * (nb / 64 + 1), st));
     sdb_count_launch();
     ns_house_qr_kernel<<<1, NS_T, 0, st>>>(P, ld, n, q, tau, F, ld, m);
     for (int j = 0; j < q; ++j) {
@@ -388,66 +462,84 @@ static int ns_enqueue(cudaStream_t st, double *S, int n, int d, int m, int kerne
         sdb_count_launch();
         ns_syr2_kernel<<<dim3((n + 31) / 32, (n + 31) / 32), 256, 0, st>>>(S, ld, n, v, z, q, j == q - 1 ? sgn : 1.0);
     }
-    if (sgn != 1.0) {
-        sdb_count_launch();
-        ns_scale_rhs_kernel<<<148, 256, 0, st>>>(F, ld, q, n, m, sgn);
-    }
-    // Cholesky of B22 = S[q:n, q:n], right-looking with a look-ahead of one panel: after the triangular solve
+    // Cholesky of B22 = S[q:n, q:n] with the right-hand sides as m extra rows (the forward substitution rides on the
+    // panel solve and the trailing update).  Right-looking with a look-ahead of one panel: after the triangular solve
     // of panel k the trailing update is split into the 64 columns of panel k+1 (main stream) and the rest (side
     // stream); panel k+1 is factored on the main stream while the rest of update k is still running.
     double *A = S + (int64_t)q * ld + q;
-    static cudaStream_t aux = nullptr;
-    static cudaEvent_t ev_trsm = nullptr, ev_rest = nullptr;
+    sdb_count_launch();
+    ns_rhs_rows_kernel<<<148, 256, 0, st>>>(F, ld, A, ld, q, nb, m, sgn);
+    // three streams: st carries the critical path  POTRF+inverse(k) -> panel solve(k) -> POTRF+inverse(k+1) ...;
+    // `nxt` updates the columns of panel k+1 below its diagonal block, `aux` the rest of the trailing matrix.
+    static cudaStream_t aux = nullptr, nxs = nullptr;
+    static cudaEvent_t ev_trsm[4], ev_rest[4], ev_next[4];
     if (!aux) {
         SDB_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
-        SDB_CUDA(cudaEventCreateWithFlags(&ev_trsm, cudaEventDisableTiming));
-        SDB_CUDA(cudaEventCreateWithFlags(&ev_rest, cudaEventDisableTiming));
+        SDB_CUDA(cudaStreamCreateWithFlags(&nxs, cudaStreamNonBlocking));
+        for (int i = 0; i < 4; ++i) {
+            SDB_CUDA(cudaEventCreateWithFlags(&ev_trsm[i], cudaEventDisableTiming));
+            SDB_CUDA(cudaEventCreateWithFlags(&ev_rest[i], cudaEventDisableTiming));
+            SDB_CUDA(cudaEventCreateWithFlags(&ev_next[i], cudaEventDisableTiming));
+        }
     }
-    bool rest_pending = false;   // a side-stream update whose completion the main stream has not yet waited for
-    for (int k0 = 0; k0 < nb; k0 += 64) {
+    // Who writes what after the panel solve of panel k (T = solved panel, T1 = its first `nxt` rows):
+    //   diagonal block of panel k+1      -= T1 T1^T         prologue of POTRF+inverse(k+1)           (st)
+    //   rest of the columns of panel k+1 -= T[nxt:] T1^T    `nxs`, awaited by the panel solve of k+1
+    //   columns of panels >= k+2         -= lower(T' T'^T)  `aux`, awaited by POTRF+inverse(k+2) and by nxs(k+1)
+    int last_rest = -1, last_next = -1;      // last panels whose aux / nxs update was issued
+    int kp = 0;
+    for (int k0 = 0; k0 < nb; k0 += 64, ++kp) {
         const int h = (nb - k0) < 64 ? (nb - k0) : 64;
+        const int rest = nb - k0 - h, restx = rest + m;     // rows below the diagonal block, with the right-hand-side rows
+        double *xinv = xinv_all + (int64_t)kp * 4096;
+        if (kp >= 2) SDB_CUDA(cudaStreamWaitEvent(st, ev_rest[(kp - 2) & 3], 0));     // issued whenever panel kp exists
         sdb_count_launch();
-        chol_potrf64_kernel<<<1, 256, 0, st>>>(A, ld, k0, h, d_info);
-        const int rest = nb - k0 - h;
-        double *xinv = xinv_all + (int64_t)(k0 / 64) * 4096;
-        sdb_count_launch();
-        chol_trinv64_kernel<<<1, 1024, 0, st>>>(A, ld, k0, h, xinv);
+        chol_potrf_inv64_kernel<<<1, 256, 0, st>>>(A, ld, k0, h, xinv, d_info, kp > 0 ? 1 : 0 SDB_PI_PROF_PASS);
+        if (last_next == kp - 1 && kp > 0) SDB_CUDA(cudaStreamWaitEvent(st, ev_next[(kp - 1) & 3], 0));
+        double *L21 = A + (int64_t)k0 * ld + k0 + h;
+        // L21 = A21 L11^{-T}:  (A21 X^T)(r, j) = sum_k A21(r, k) X(j, k),  X(j, k) = xinv[k*64 + j]
+        int rc = sdb_gemm_k64_inplace(st, restx, h, L21, ld, xinv, 64);
+        if (rc) return rc;
         if (rest > 0) {
-            double *L21 = A + (int64_t)k0 * ld + k0 + h;
-            // L21 = A21 L11^{-T}:  (A21 X^T)(r, j) = sum_k A21(r, k) X(j, k),  X(j, k) = xinv[k*64 + j]
-            int rc2 = sdb_gemm_k64_inplace(st, rest, h, L21, ld, xinv, 64);
-            if (rc2) return rc2;
+            SDB_CUDA(cudaEventRecord(ev_trsm[kp & 3], st));
             double *A22 = A + (int64_t)(k0 + h) * ld + k0 + h;
-            const int nxt = rest < 64 ? rest : 64;      // columns of the next panel
-            // the previous side-stream update also wrote into the columns touched from here on
-            if (rest_pending) { SDB_CUDA(cudaStreamWaitEvent(st, ev_rest, 0)); rest_pending = false; }
-            SDB_CUDA(cudaEventRecord(ev_trsm, st));
-            int rc = sdb_gemm_k64_launch<true, false, false>(st, rest, nxt, h, L21, L21, A22, ld, ld);     // next panel's columns
+            const int nxt = rest < 64 ? rest : 64;      // columns of the next panel = rows of its diagonal block
+            SDB_CUDA(cudaStreamWaitEvent(nxs, ev_trsm[kp & 3], 0));
+            if (last_rest >= 0) SDB_CUDA(cudaStreamWaitEvent(nxs, ev_rest[last_rest & 3], 0));   // aux(kp-1) wrote these columns too
+            rc = sdb_gemm_k64_launch<true, false, false>(nxs, restx - nxt, nxt, h, L21 + nxt, L21, A22 + nxt, ld, ld);
             if (rc) return rc;
+            SDB_CUDA(cudaEventRecord(ev_next[kp & 3], nxs));
+            last_next = kp;
             if (rest > 64) {
-                SDB_CUDA(cudaStreamWaitEvent(aux, ev_trsm, 0));
-                rc = sdb_syrk_k64_update(aux, rest - 64, rest - 64, h, L21 + 64, L21 + 64, A22 + (int64_t)64 * ld + 64, ld);
+                SDB_CUDA(cudaStreamWaitEvent(aux, ev_trsm[kp & 3], 0));
+                rc = sdb_syrk_k64_update(aux, restx - 64, rest - 64, h, L21 + 64, L21 + 64, A22 + (int64_t)64 * ld + 64, ld);
                 if (rc) return rc;
-                SDB_CUDA(cudaEventRecord(ev_rest, aux));
-                rest_pending = true;
+                SDB_CUDA(cudaEventRecord(ev_rest[kp & 3], aux));
+                last_rest = kp;
             }
         }
     }
-    if (rest_pending) SDB_CUDA(cudaStreamWaitEvent(st, ev_rest, 0));
-    // (s B22) y2 = s g2: forward with L, backward with L^T; right-hand sides in F[q:n], result back in F[q:n]
-    double *G2 = F + q;
-    for (int k0 = 0; k0 < nb; k0 += 64) {
-        const int h = (nb - k0) < 64 ? (nb - k0) : 64;
-        const int rest = nb - k0 - h;
+    // join the side streams (the last panel solve already waited for the last nxs update)
+    if (last_rest >= 0) SDB_CUDA(cudaStreamWaitEvent(st, ev_rest[last_rest & 3], 0));
+    if (last_next >= 0) SDB_CUDA(cudaStreamWaitEvent(st, ev_next[last_next & 3], 0));
+    // L^T x = y (y = rows nb.. of A), x -> F[q:n]
+    {
+        static int per_sm = 0;
+        if (!per_sm) SDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_bwd_flags_kernel, 256, 0));
+        sdb_device_props dp;
+        int rc = sdb_get_device_props(&dp);
+        if (rc) return rc;
+        const int nblk = (nb + 63) / 64;
+        int grid = dp.sm_count * (per_sm > 2 ? 2 : per_sm);
+        if (grid > nblk) grid = nblk;
+        if (grid < 1) { sdb_set_error("sdb_rbf_fit_nullspace: the backward-solve kernel does not fit on the device"); return SDB_ERR_CUDA; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeCooperative; at.val.cooperative = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
         sdb_count_launch();
-        chol_fwd_kernel<<<rest > 0 ? (rest + 255) / 256 : 1, 256, 0, st>>>(A, ld, xinv_all + (int64_t)(k0 / 64) * 4096, G2, xf, ld, k0,
-                                                                           h, nb, m);
-    }
-    for (int k0 = ((nb - 1) / 64) * 64; k0 >= 0; k0 -= 64) {
-        const int h = (nb - k0) < 64 ? (nb - k0) : 64;
-        sdb_count_launch();
-        chol_bwd_kernel<<<k0 > 0 ? (k0 + 255) / 256 : 1, 256, 0, st>>>(A, ld, xinv_all + (int64_t)(k0 / 64) * 4096, xf, G2, ld, k0, h,
-                                                                       m);
+        SDB_CUDA(cudaLaunchKernelEx(&cfg, chol_bwd_flags_kernel, (const double *)A, ld, (const double *)xinv_all, F + q, ld, nb, m, ready));
     }
     sdb_count_launch();
     ns_finish_kernel<<<m, NS_T, 0, st>>>(S, ld, n, q, tau, F, ld, m, COEFS);
@@ -456,9 +548,9 @@ static int ns_enqueue(cudaStream_t st, double *S, int n, int d, int m, int kerne
 }
 
 extern "C" int64_t sdb_rbf_fit_nullspace_work(int64_t n, int32_t d, int32_t m) {
-    const int64_t N = n + d + 1;
-    // system | right-hand sides | tau, v, w, z | forward-solve result | inverses of the diagonal blocks
-    return N * N + N * m + 3 * n + 128 + N * m + (n / 64 + 2) * 4096;
+    const int64_t N = n + d + 1, ld = ns_ld(n, d, m);
+    // system (N columns of ld) | right-hand sides | tau, v, w, z | inverses of the diagonal blocks | block flags
+    return ld * N + ld * m + 3 * n + 128 + (n / 64 + 2) * 4096 + (n / 64 + 2) / 2 + 8;
 }
 
 // Same contract as sdb_rbf_fit (X [n x d], Y [n x m] -> d_COEFS [(n+d+1) x m] row-major) for kernel types
@@ -471,15 +563,15 @@ extern "C" int sdb_rbf_fit_nullspace(const double *d_X, const double *d_Y, int64
                   "sdb_rbf_fit_nullspace: kernel_type %d is not conditionally definite with a linear tail (use sdb_rbf_fit)", kernel_type);
     SDB_CHECK_ARG(n > d + 1, "sdb_rbf_fit_nullspace: needs more than d + 1 points");
     SDB_CHECK_LIMIT(d >= 1 && d <= SDB_MAX_D && m >= 1 && m <= SDB_MAX_M, "sdb_rbf_fit_nullspace: d=%d m=%d outside limits", d, m);
-    const int64_t N = n + d + 1;
+    const int64_t N = n + d + 1, ld = ns_ld(n, d, m);
     double *S = d_work;
-    double *F = S + N * N;
-    double *vec = F + N * m;
+    double *F = S + ld * N;
+    double *vec = F + ld * m;
     cudaStream_t st = (cudaStream_t)stream;
     auto enqueue = [&]() -> int {
-        int rc = sdb_rbf_system(d_X, d_Y, n, d, m, kernel_type, S, F, stream);
+        int rc = sdb_rbf_system_ld(d_X, d_Y, n, d, m, kernel_type, S, F, ld, stream);
         if (rc) return rc;
-        return ns_enqueue(st, S, (int)n, d, m, kernel_type, F, d_COEFS, vec, d_info);
+        return ns_enqueue(st, S, ld, (int)n, d, m, kernel_type, F, d_COEFS, vec, d_info);
     };
     if (n < 256) return enqueue();
     sdb_graph_key key = {{d_X, d_Y, d_COEFS, d_work, d_info}, {n, d, m, kernel_type}, 2, 0};

@@ -43,6 +43,9 @@ struct sdb_device_props {
     int sm_count, cc_major, cc_minor, smem_optin;
 };
 int sdb_get_device_props(sdb_device_props *out);  // cached per device
+// sdb_rbf_system with an explicit leading dimension (sdb_fit.cu; used by the null-space solver)
+int sdb_rbf_system_ld(const double *d_X, const double *d_Y, int64_t n, int32_t d, int32_t m, int32_t kernel_type, double *d_S,
+                      double *d_RHS, int64_t ld, void *stream);
 
 // ---------------------------------------------------------------------------------------
 // Philox-4x32-10 (Salmon et al. 2011), counter-based: no state is carried between steps.

@@ -279,9 +279,10 @@ __device__ __forceinline__ double ref_phi(double r, int kt) {
     }
 }
 
-// S [(n+d+1)^2] (symmetric, so row- and column-major coincide) and RHS as m contiguous columns [m][n+d+1].
+// S [(n+d+1) columns of ld >= n+d+1] (symmetric, so row- and column-major coincide) and RHS as m columns of ld.
 __global__ void __launch_bounds__(256) rbf_system_kernel(const double *__restrict__ X, const double *__restrict__ Y, int n, int d,
-                                                         int m, int kt, double *__restrict__ S, double *__restrict__ RHS) {
+                                                         int m, int kt, double *__restrict__ S, double *__restrict__ RHS,
+                                                         int64_t ld) {
     const int N = n + d + 1;
     const int i = blockIdx.x * 16 + (threadIdx.x & 15);  // fast index: contiguous in memory
     const int j = blockIdx.y * 16 + (threadIdx.x >> 4);
@@ -291,24 +292,31 @@ __global__ void __launch_bounds__(256) rbf_system_kernel(const double *__restric
         else if (i < n) v = (j - n < d) ? X[(size_t)i * d + (j - n)] : 1.0;
         else if (j < n) v = (i - n < d) ? X[(size_t)j * d + (i - n)] : 1.0;
         else v = 0.0;
-        S[(size_t)j * N + i] = v;
+        S[(size_t)j * ld + i] = v;
     }
     if (RHS && blockIdx.y == 0 && (threadIdx.x >> 4) == 0 && i < N)
-        for (int k = 0; k < m; ++k) RHS[(size_t)k * N + i] = i < n ? Y[(size_t)i * m + k] : 0.0;
+        for (int k = 0; k < m; ++k) RHS[(size_t)k * ld + i] = i < n ? Y[(size_t)i * m + k] : 0.0;
 }
 
-extern "C" int sdb_rbf_system(const double *d_X, const double *d_Y, int64_t n, int32_t d, int32_t m, int32_t kernel_type,
-                              double *d_S, double *d_RHS, void *stream) {
+// the system with a leading dimension ld >= n + d + 1 (rows beyond n + d + 1 are left untouched)
+int sdb_rbf_system_ld(const double *d_X, const double *d_Y, int64_t n, int32_t d, int32_t m, int32_t kernel_type, double *d_S,
+                      double *d_RHS, int64_t ld, void *stream) {
     SDB_CHECK_ARG(d_X && d_S && (d_Y || !d_RHS), "sdb_rbf_system: NULL pointer");
     SDB_CHECK_ARG(n >= 1 && n < (1 << 30), "sdb_rbf_system: n out of range");
     SDB_CHECK_LIMIT(d >= 1 && d <= SDB_MAX_D && m >= 1 && m <= SDB_MAX_M, "sdb_rbf_system: d=%d m=%d outside limits", d, m);
     SDB_CHECK_ARG(kernel_type >= 0 && kernel_type <= 7, "sdb_rbf_system: kernel_type %d outside [0,7]", kernel_type);
     const int N = (int)n + d + 1;
+    SDB_CHECK_ARG(ld >= N, "sdb_rbf_system: leading dimension below n + d + 1");
     dim3 grid((N + 15) / 16, (N + 15) / 16);
     sdb_count_launch();
-    rbf_system_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_X, d_Y, (int)n, d, m, kernel_type, d_S, d_RHS);
+    rbf_system_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_X, d_Y, (int)n, d, m, kernel_type, d_S, d_RHS, ld);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
+}
+
+extern "C" int sdb_rbf_system(const double *d_X, const double *d_Y, int64_t n, int32_t d, int32_t m, int32_t kernel_type,
+                              double *d_S, double *d_RHS, void *stream) {
+    return sdb_rbf_system_ld(d_X, d_Y, n, d, m, kernel_type, d_S, d_RHS, n + d + 1, stream);
 }
 
 __global__ void __launch_bounds__(256) transpose_out_kernel(const double *__restrict__ Xc, int N, int m, double *__restrict__ out) {

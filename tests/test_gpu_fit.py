@@ -280,7 +280,7 @@ def test_rbf_nullspace_cholesky_matches_direct(L):
     from surrdamh_b200 import surrogate_rbf as SR
     rs = np.random.RandomState(8)
     for d, m, n, kt in ((2, 1, 900, 1), (4, 3, 700, 1), (3, 2, 500, 0), (4, 3, 400, 4), (4, 3, 400, 5), (8, 2, 300, 6),
-                        (2, 1, 2100, 1), (32, 3, 600, 1)):
+                        (2, 1, 2100, 1), (32, 3, 600, 1), (2, 5, 700, 1), (1, 4, 330, 0)):
         X = rs.standard_normal((n, d))
         Y = np.stack([np.sin((k + 1) * X).sum(axis=1) for k in range(m)], axis=1)
         up = SR.Surrogate_update(d, m, kernel_type=kt, solver_type="nullspace")
