@@ -258,13 +258,16 @@ extern "C" int sdb_poly_fit(const double *d_X, const double *d_Y, int64_t n, int
 // ===================================================================================================
 // distance exactly as the reference forms it: sum_k (x_jk - x_ik)^2 with separately rounded
 // square and add (np.power(Q-T, 2) accumulated k = 0..d-1), then an IEEE square root.
-__device__ __forceinline__ double ref_distance(const double *__restrict__ xi, const double *__restrict__ xj, int d) {
+__device__ __forceinline__ double ref_sumsq(const double *__restrict__ xi, const double *__restrict__ xj, int d) {
     double s = 0.0;
     for (int k = 0; k < d; ++k) {
         const double df = __dadd_rn(xj[k], -xi[k]);
         s = __dadd_rn(s, __dmul_rn(df, df));
     }
-    return __dsqrt_rn(s);
+    return s;
+}
+__device__ __forceinline__ double ref_distance(const double *__restrict__ xi, const double *__restrict__ xj, int d) {
+    return __dsqrt_rn(ref_sumsq(xi, xj, d));
 }
 
 __device__ __forceinline__ double ref_phi(double r, int kt) {
@@ -477,6 +480,143 @@ __global__ void __launch_bounds__(1024, 1) thin_remove_kernel(const double *__re
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The removal loop when everything fits in shared memory -- the normal case (n up to ~8000 points for d = 2).
+// The loop is a chain of reductions over n, so it is bound by INSTRUCTIONS ISSUED per point, and this version is
+// built to issue few of them:
+//   * a removed point is "poisoned" in the CTA's private copy (coordinate 0 := 1e150 -> every distance to it is
+//     ~1e150, finite so that the square root stays on its fast path; nn_dist := +inf), so no scan tests an alive flag;
+//   * D is a template parameter (vector loads, unrolled differences);
+//   * (distance, index) arg-min: distances are non-negative, so their bit patterns order like unsigned integers
+//     and a warp reduces with three REDUX instructions (high word, low word, index) instead of five shuffle
+//     rounds of a (double, int) pair; the 16 per-warp results are combined by every warp redundantly (no second
+//     barrier for a broadcast).
+// Same decisions as thin_remove_kernel: distance = correctly rounded square root of the reference's sum of
+// squares, ties -> smallest index.
+// ---------------------------------------------------------------------------------------------------
+#define THF_T 512
+#define THF_POISON 1e150
+
+struct thf_red { unsigned hi[2][16], lo[2][16]; int idx[2][16]; };
+
+__device__ __forceinline__ void thf_argmin(double &best, int &bidx, thf_red &R, int buf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned hi = (unsigned)__double2hiint(best), lo = (unsigned)__double2loint(best);
+    {
+        const unsigned hm = __reduce_min_sync(0xffffffffu, hi);
+        const unsigned lm = __reduce_min_sync(0xffffffffu, hi == hm ? lo : 0xffffffffu);
+        const int im = __reduce_min_sync(0xffffffffu, (hi == hm && lo == lm) ? bidx : INT_MAX);
+        if (lane == 0) { R.hi[buf][warp] = hm; R.lo[buf][warp] = lm; R.idx[buf][warp] = im; }
+    }
+    __syncthreads();
+    const bool in = lane < (THF_T >> 5);
+    hi = in ? R.hi[buf][lane] : 0xffffffffu;
+    lo = in ? R.lo[buf][lane] : 0xffffffffu;
+    const int id = in ? R.idx[buf][lane] : INT_MAX;
+    const unsigned hm = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned lm = __reduce_min_sync(0xffffffffu, hi == hm ? lo : 0xffffffffu);
+    bidx = __reduce_min_sync(0xffffffffu, (hi == hm && lo == lm) ? id : INT_MAX);
+    best = __hiloint2double((int)hm, (int)lm);
+}
+
+template <int D>
+__global__ void __launch_bounds__(THF_T, 1) thin_remove_fast_kernel(const double *__restrict__ Xg, int n, int dd, int no_keep,
+                                                                    const double *__restrict__ nn_dist_g,
+                                                                    const int *__restrict__ nn_idx_g, uint8_t *__restrict__ keep_g) {
+    extern __shared__ __align__(16) unsigned char thin_sm[];
+    __shared__ thf_red R;
+    __shared__ int todo[1024];
+    __shared__ int ntodo;
+    const int d = D ? D : dd;
+    const int tid = threadIdx.x;
+    double *Xs = (double *)thin_sm;
+    double *nn_dist = Xs + (size_t)n * d;
+    int *nn_idx = (int *)(nn_dist + n);
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    for (int e = tid; e < n * d; e += THF_T) Xs[e] = Xg[e];
+    for (int i = tid; i < n; i += THF_T) {
+        const int j = nn_idx_g[i];
+        nn_idx[i] = j;
+        nn_dist[i] = j == INT_MAX ? INF : nn_dist_g[i];
+        keep_g[i] = 1;
+    }
+    if (tid == 0) ntodo = 0;
+    __syncthreads();
+    int buf = 0;
+    for (int it = 0; it < n - no_keep; ++it) {
+        // global minimum of the nearest-neighbour distances; ties -> smallest row (the first flat arg-min of the reference)
+        double best = INF;
+        int brow = INT_MAX;
+#pragma unroll 4
+        for (int i = tid; i < n; i += THF_T) {
+            const double di = nn_dist[i];
+            const bool lt = di < best;          // i ascending per thread: the first minimum is kept
+            best = lt ? di : best;
+            brow = lt ? i : brow;
+        }
+        thf_argmin(best, brow, R, buf);
+        buf ^= 1;
+        const int v = brow;
+        if (v == INT_MAX) break;                // fewer than two alive points (uniform)
+        if (tid == 0) { keep_g[v] = 0; Xs[(size_t)v * d] = THF_POISON; nn_dist[v] = INF; nn_idx[v] = INT_MAX; }
+        // rows whose nearest neighbour was the victim must be rescanned (usually one or two)
+        bool again;
+        do {
+#pragma unroll 4
+            for (int i = tid; i < n; i += THF_T)
+                if (nn_idx[i] == v && i != v) {
+                    const int slot = atomicAdd(&ntodo, 1);
+                    if (slot < 1024) todo[slot] = i;
+                }
+            __syncthreads();                     // also publishes the poisoned coordinates of v
+            const int found = ntodo;
+            again = found > 1024;
+            const int cnt = again ? 1024 : found;
+            for (int t = 0; t < cnt; ++t) {      // the whole CTA scans one row at a time
+                const int row = todo[t];
+                double xr[D ? D : 1];
+                if (D) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) xr[k] = Xs[(size_t)row * D + k];
+                }
+                double b = INF;
+                int bj = INT_MAX;
+#pragma unroll 4
+                for (int j = tid; j < n; j += THF_T) {
+                    double sq = 0.0;
+                    if (D == 2) {
+                        const double2 p = *(const double2 *)(Xs + (size_t)j * 2);
+                        const double d0 = __dadd_rn(p.x, -xr[0]), d1 = __dadd_rn(p.y, -xr[1]);
+                        sq = __dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1));      // 0 + d0^2 == d0^2 exactly
+                    } else if (D) {
+#pragma unroll
+                        for (int k = 0; k < D; ++k) {
+                            const double df = __dadd_rn(Xs[(size_t)j * D + k], -xr[k]);
+                            sq = __dadd_rn(sq, __dmul_rn(df, df));
+                        }
+                    } else {
+                        sq = ref_sumsq(Xs + (size_t)row * d, Xs + (size_t)j * d, d);
+                    }
+                    const double r = __dsqrt_rn(sq);
+                    const bool lt = r < b && j != row;
+                    b = lt ? r : b;
+                    bj = lt ? j : bj;
+                }
+                thf_argmin(b, bj, R, buf);
+                buf ^= 1;
+                if (tid == 0) {                   // only poisoned points left: nobody else is alive
+                    const bool none = !(b < 0.5 * THF_POISON);
+                    nn_dist[row] = none ? INF : b;
+                    nn_idx[row] = none ? INT_MAX : bj;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) ntodo = 0;
+            __syncthreads();
+        } while (again);
+    }
+}
+
 extern "C" int64_t sdb_rbf_thin_work(int64_t n) { return n + n / 2 + 64; }
 
 extern "C" int sdb_rbf_thin(const double *d_X, int64_t n, int32_t d, int64_t no_keep, uint8_t *d_keep, double *d_work,
@@ -496,6 +636,17 @@ extern "C" int sdb_rbf_thin(const double *d_X, int64_t n, int32_t d, int64_t no_
     sdb_device_props dp;
     int rc = sdb_get_device_props(&dp);
     if (rc) return rc;
+    const size_t need_fast = (size_t)n * ((size_t)d * 8 + 8 + 4) + 16;
+    if (need_fast + 12288 <= (size_t)dp.smem_optin) {
+        void (*fn)(const double *, int, int, int, const double *, const int *, uint8_t *) =
+            d == 1 ? thin_remove_fast_kernel<1> : d == 2 ? thin_remove_fast_kernel<2> : d == 3 ? thin_remove_fast_kernel<3>
+            : d == 4 ? thin_remove_fast_kernel<4> : thin_remove_fast_kernel<0>;
+        SDB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_fast));
+        sdb_count_launch();
+        fn<<<1, THF_T, need_fast, st>>>(d_X, (int)n, d, (int)no_keep, nn_dist, nn_idx, d_keep);
+        SDB_CUDA(cudaGetLastError());
+        return SDB_OK;
+    }
     const size_t need = (size_t)n * ((size_t)d * 8 + 8 + 4 + 1) + 16;
     const int use_smem = need + 8192 <= (size_t)dp.smem_optin;
     SDB_CUDA(cudaFuncSetAttribute((const void *)thin_remove_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
