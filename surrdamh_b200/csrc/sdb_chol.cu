@@ -506,7 +506,7 @@ static int ns_enqueue(cudaStream_t st, double *S, int64_t ld, int n, int d, int 
             const int nxt = rest < 64 ? rest : 64;      // columns of the next panel = rows of its diagonal block
             SDB_CUDA(cudaStreamWaitEvent(nxs, ev_trsm[kp & 3], 0));
             if (last_rest >= 0) SDB_CUDA(cudaStreamWaitEvent(nxs, ev_rest[last_rest & 3], 0));   // aux(kp-1) wrote these columns too
-            rc = sdb_gemm_k64_launch<true, false, false>(nxs, restx - nxt, nxt, h, L21 + nxt, L21, A22 + nxt, ld, ld);
+            rc = sdb_gemm_k64_skinny_update(nxs, restx - nxt, nxt, h, L21 + nxt, L21, A22 + nxt, ld, ld);
             if (rc) return rc;
             SDB_CUDA(cudaEventRecord(ev_next[kp & 3], nxs));
             last_next = kp;

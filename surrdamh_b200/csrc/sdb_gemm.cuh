@@ -303,6 +303,73 @@ static inline int sdb_gemm_k64_launch(cudaStream_t st, int M, int N, int K, cons
     return SDB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The same products for a SKINNY result (N, K <= 64 and a tall M): the panel solve and the next-panel column update
+// of the Cholesky sit on its critical path, and with 128 x 64 tiles a 4096 x 64 result keeps only 32 SMs busy for the
+// ~4 us a tile's 2048 DMMAs take.  Here a CTA owns 32 rows (4 warps x 8 rows): the A fragments go straight from
+// global memory into registers (a warp reads its 8 x 64 slice once), only B passes through shared memory, and each
+// warp runs 8 independent accumulator chains (a dependent DMMA has ~150 cycles of latency).  In place (C == A) is
+// safe: a warp reads exactly the rows it later writes.  B(k, j) = B[k*ldb + j].
+// ---------------------------------------------------------------------------------------------------
+#define GS_BS 68     // row stride of B in shared memory: == 4 (mod 16) doubles -> conflict-free fragment loads
+
+template <bool ASSIGN>
+static __global__ void __launch_bounds__(128) sdb_gemm_skinny64_kernel(const double *A, const double *__restrict__ B, double *C,
+                                                                       int64_t ld, int64_t ldb, int M, int N, int K) {
+    __shared__ __align__(16) double Bt[64][GS_BS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    const int row = blockIdx.x * 32 + warp * 8 + gid;
+    const bool rok = row < M;
+    double breg[32];
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {                           // 64 x 64 elements of B, 32 per thread, all loads in flight
+        const int e = tid + u * 128, n = e & 63, k = e >> 6;
+        breg[u] = (n < N && k < K) ? B[(int64_t)k * ldb + n] : 0.0;
+    }
+    double a[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const int k = 4 * s + tig;
+        const double v = (rok && k < K) ? A[(int64_t)k * ld + row] : 0.0;
+        a[s] = ASSIGN ? v : -v;
+    }
+    double acc[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int n = j * 8 + tig * 2 + e;
+            acc[j][e] = (!ASSIGN && rok && n < N) ? C[(int64_t)n * ld + row] : 0.0;
+        }
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+        const int e = tid + u * 128;
+        Bt[e >> 6][e & 63] = breg[u];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 16; ++s)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sdb_dmma(acc[j][0], acc[j][1], a[s], Bt[4 * s + tig][j * 8 + gid]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int n = j * 8 + tig * 2 + e;
+            if (rok && n < N) C[(int64_t)n * ld + row] = acc[j][e];
+        }
+}
+
+template <bool ASSIGN>
+static inline int sdb_gemm_skinny64_launch(cudaStream_t st, int M, int N, int K, const double *A, const double *B, double *C,
+                                           int64_t ld, int64_t ldb) {
+    if (M <= 0 || N <= 0 || K <= 0) return SDB_OK;
+    sdb_count_launch();
+    sdb_gemm_skinny64_kernel<ASSIGN><<<(M + 31) / 32, 128, 0, st>>>(A, B, C, ld, ldb, M, N, K);
+    SDB_CUDA(cudaGetLastError());
+    return SDB_OK;
+}
+
 // C -= A B, B = U12 (k-contiguous): the LU trailing update
 static inline int sdb_gemm_k64_update(cudaStream_t st, int M, int N, int K, const double *A, const double *B, double *C,
                                       int64_t ld) {
@@ -316,5 +383,10 @@ static inline int sdb_syrk_k64_update(cudaStream_t st, int M, int N, int K, cons
 // A (M x K, leading dimension ld) := A * Xt with Xt(k, j) = X[k*ldx + j], K, N <= 64: the triangular solve of the
 // Cholesky panel as a multiplication by the inverse of the diagonal block, in place
 static inline int sdb_gemm_k64_inplace(cudaStream_t st, int M, int K, double *A, int64_t ld, const double *X, int64_t ldx) {
-    return sdb_gemm_k64_launch<true, false, true>(st, M, K, K, A, X, A, ld, ldx);
+    return sdb_gemm_skinny64_launch<true>(st, M, K, K, A, X, A, ld, ldx);
+}
+// C (M x N, N <= 64) -= A (M x K) B with B(k, j) = B[k*ldb + j], K <= 64: the next panel's columns of the Cholesky
+static inline int sdb_gemm_k64_skinny_update(cudaStream_t st, int M, int N, int K, const double *A, const double *B, double *C,
+                                             int64_t ld, int64_t ldb) {
+    return sdb_gemm_skinny64_launch<false>(st, M, N, K, A, B, C, ld, ldb);
 }

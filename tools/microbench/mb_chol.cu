@@ -64,7 +64,7 @@ int main() {
     for (int M : {4096, 2048, 512, 64}) {
         float us = time_loop(st, reps, [&](int i) { sdb_gemm_k64_inplace(st, M, 64, A + 64, ld, xinv, 64); });
         printf("trsm-as-gemm M=%d: %.2f us\n", M, us);
-        us = time_loop(st, reps, [&](int i) { sdb_gemm_k64_launch<true, false, false>(st, M, 64, 64, A + 64, A + 64, A + 64 * ld + 64, ld, ld); });
+        us = time_loop(st, reps, [&](int i) { sdb_gemm_k64_skinny_update(st, M, 64, 64, A + 64, A + 64, A + 64 * ld + 64, ld, ld); });
         printf("next-columns gemm M=%d: %.2f us\n", M, us);
         us = time_loop(st, reps, [&](int i) { sdb_syrk_k64_update(st, M, M, 64, A + 64, A + 64, A + 64 * ld + 64, ld); });
         printf("syrk M=%d: %.2f us  (%.2f TF/s)\n", M, us, (double)M * M * 64 / (us * 1e-6) / 1e12);
