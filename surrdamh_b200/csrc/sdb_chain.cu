@@ -668,8 +668,10 @@ static int plan(const sdb_chain_args *a, int *L_out, int *threads_out, int *bloc
     const int64_t blocks = (lanes + threads - 1) / threads;
     size_t smem_req = smem;
     if (a->coresident) {
-        // more than half of the shared memory per CTA -> at most one CTA of this kernel per SM; the rest of the SM
-        // (registers: 64 per thread here; shared memory: what is left) stays available to other streams
+        // more than half of the shared memory per CTA -> at most one CTA of this kernel per SM, i.e. the CTAs run in two
+        // waves and the second wave leaves a few SMs (and, on every SM, ~8 K registers and ~110 KB of shared memory) to
+        // the kernels of other streams.  Measured: making more room (224-thread CTAs, so that the refit kernels really
+        // co-reside) slows this kernel by 8 % and the FP64-latency-bound refit still runs 4-5 x slower beside it.
         const size_t half = (size_t)dp.smem_optin / 2 + 2048;
         if (smem_req < half) smem_req = half;
     }

@@ -17,7 +17,9 @@
 #include "sdb_gemm.cuh"
 #include "sdb_graph.cuh"
 
-#define NS_T 1024
+// 512 threads x <= 64 registers: these single-CTA kernels must fit beside a resident chain CTA (448 threads x 64
+// registers) when the refit runs concurrently with the next block of chain steps
+#define NS_T 512
 
 __device__ __forceinline__ double ns_block_sum(double v, double *scratch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -37,7 +39,7 @@ __device__ __forceinline__ double ns_block_sum(double v, double *scratch) {
 // diagonal (v_j(j) = 1 implicit), R on and above it, tau[q].  Q^T is applied to the m columns of F (ldf).
 // One CTA: the norm of column j is a block reduction; the remaining columns are handled one per warp.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NS_T, 1) ns_house_qr_kernel(double *__restrict__ P, int64_t ldp, int n, int q,
+__global__ void __launch_bounds__(NS_T, 2) ns_house_qr_kernel(double *__restrict__ P, int64_t ldp, int n, int q,
                                                               double *__restrict__ tau, double *__restrict__ F, int64_t ldf, int m) {
     __shared__ double scratch[32];
     __shared__ double s_tau, s_scale, s_beta;
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(256) ns_symv_kernel(const double *__restrict__
 }
 
 // z = tau w - (tau^2 (v.w) / 2) v
-__global__ void __launch_bounds__(NS_T, 1) ns_z_kernel(int n, const double *__restrict__ v, const double *__restrict__ w,
+__global__ void __launch_bounds__(NS_T, 2) ns_z_kernel(int n, const double *__restrict__ v, const double *__restrict__ w,
                                                        const double *__restrict__ tau, int j, double *__restrict__ z) {
     __shared__ double scratch[32];
     double a = 0.0;
@@ -132,18 +134,24 @@ __global__ void __launch_bounds__(256) ns_syr2_kernel(double *__restrict__ Phi, 
 // ---------------------------------------------------------------------------------------------------
 // Cholesky (lower, column-major, leading dimension ld) of the nb x nb matrix A, 64-column blocks
 // ---------------------------------------------------------------------------------------------------
-// POTRF + inverse of the 64 x 64 diagonal block, blocked by FOUR columns: the trailing matrix and the growing
-// inverse live in DMMA accumulator fragments (8 x 8 blocks, lower block triangle: every warp owns one block row of A
-// and the complementary block row of X), one warp factors the 64 x 4 panel with shuffles only (no block barrier inside the
-// panel), and the rank-4 updates  A -= Lp Lp^T,  X -= Lp Xr  are m8n8k4 DMMAs whose operands are two small
-// k-major panels in shared memory.  Two block barriers per FOUR columns; shared-memory traffic per column is a
-// few hundred bytes instead of the 8 KB a register-tiled rank-1 update reads back.
+// POTRF + inverse of the 64 x 64 diagonal block, blocked by FOUR columns, as a producer / consumer pipeline.
+//   workers (warps 0..7): the trailing matrix and the growing inverse live in their DMMA accumulator fragments
+//       (8 x 8 blocks, lower block triangle: every warp owns one block row of A and the complementary block row of X);
+//       the rank-4 updates  A -= Lp Lp^T,  X -= Lp Xr  are m8n8k4 DMMAs whose operands are two small k-major panels
+//       in shared memory (double-buffered);
+//   panel warps (8: L, 9: X): factor the 64 x 4 panel / the 4 x 64 rows of X.  Every lane factors the 4 x 4 pivot
+//       block redundantly in registers (broadcast loads, no shuffles): the serial chain is four reciprocal roots.
+// Look-ahead inside the kernel: after panel s the workers FIRST update and hand over the four columns / rows of
+// panel s+1 (named barrier 2), then finish the rest of update s while the panel warps already factor panel s+1
+// (named barrier 1 hands the factored panel back).  A dependent DMMA has ~150 cycles of latency, a dependent DFMA 8:
+// the serial chain therefore contains one DMMA per panel, everything else of the update overlaps with it.
 // upd != 0: the block first receives the previous panel's contribution  D -= T T^T,  T = A[k0.., k0-64..k0-1]
 // (the rows of the previous panel solve that face this block), also as DMMAs -- the look-ahead update of the
 // diagonal block is done HERE, so the factorisation's critical path never waits for the panel-wide update kernel.
 // ---------------------------------------------------------------------------------------------------
 #define PI_S 68      // row stride of the k-major panels: == 4 (mod 16) doubles -> conflict-free fragment loads
 #define PI_XS 65     // column stride of the staged inverse: row-wise stores by 32 lanes hit 32 distinct banks
+#define PI_T 320     // 8 worker warps + 2 panel warps
 
 #ifndef SDB_PI_PROF_ARG
 #define SDB_PI_PROF_ARG
@@ -152,90 +160,41 @@ __global__ void __launch_bounds__(256) ns_syr2_kernel(double *__restrict__ Phi, 
 #define SDB_PI_STAMP(i)
 #define SDB_PI_PROF_END
 #endif
-__global__ void __launch_bounds__(256, 1) chol_potrf_inv64_kernel(double *__restrict__ A, int64_t ld, int k0, int h,
-                                                                  double *__restrict__ Xout, int *__restrict__ info, int upd SDB_PI_PROF_ARG) {
+
+__device__ __forceinline__ void pi_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void pi_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+__global__ void __launch_bounds__(PI_T, 1) chol_potrf_inv64_kernel(double *__restrict__ A, int64_t ld, int k0, int h,
+                                                                   double *__restrict__ Xout, int *__restrict__ info, int upd SDB_PI_PROF_ARG) {
     SDB_PI_PROF_INIT
-    __shared__ __align__(16) double sm[(64 + 16) * PI_S];
+    __shared__ __align__(16) double sm[(64 + 24) * PI_S];
     double (*T)[PI_S] = (double (*)[PI_S])sm;              // prologue: T[k][i]; afterwards the staged inverse Xs[c*PI_XS + i]
     double *Xs = sm;
-    double (*Lp)[PI_S] = T + 64;                            // final L(:, j0..j0+3), k-major
-    double (*Xr)[PI_S] = Lp + 4;                            // final X(j0..j0+3, :)
-    double (*Pn)[PI_S] = Xr + 4;                            // the panel as extracted from the accumulators (not yet factored)
+    double (*LpB)[PI_S] = T + 64;                           // [2][4]: final L(:, j0..j0+3), k-major, double-buffered
+    double (*XrB)[PI_S] = LpB + 8;                          // [2][4]: final X(j0..j0+3, :)
+    double (*Pn)[PI_S] = XrB + 8;                           // the panel as extracted from the accumulators (not yet factored)
     double (*Xn)[PI_S] = Pn + 4;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, gid = lane >> 2, tig = lane & 3;
-    // block rows: warps w and w + 4 share a scheduler, so their rows pair up as (0,7) (1,6) (2,5) (3,4)
-    const int ra = w < 4 ? w : 11 - w, bx = 7 - ra;
-    double ca[8][2], cx[8][2];
-    if (upd) {
-        double tv[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {                      // all sixteen loads in flight before the first store
-            const int e = tid + u * 256, i = e & 63, c = e >> 6;
-            tv[u] = i < h ? A[(int64_t)(k0 - 64 + c) * ld + k0 + i] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int e = tid + u * 256;
-            T[e >> 6][e & 63] = tv[u];
-        }
-    }
-    for (int e = tid; e < 4 * PI_S; e += 256) (&Xn[0][0])[e] = 0.0;      // columns right of the diagonal block are never written
-#pragma unroll
-    for (int bj = 0; bj < 8; ++bj)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int i = ra * 8 + gid, c = bj * 8 + tig * 2 + e;
-            ca[bj][e] = (bj <= ra) ? ((i < h && c < h) ? A[(int64_t)(k0 + c) * ld + k0 + i] : (i == c ? 1.0 : 0.0)) : 0.0;
-            cx[bj][e] = (bx * 8 + gid == c) ? 1.0 : 0.0;
-        }
-    __syncthreads();
-    if (upd) {
-#pragma unroll 2
-        for (int kk = 0; kk < 64; kk += 4) {
-            const double fa = -T[kk + tig][ra * 8 + gid];
-#pragma unroll
-            for (int bj = 0; bj < 8; ++bj)
-                if (bj <= ra) sdb_dmma(ca[bj][0], ca[bj][1], fa, T[kk + tig][bj * 8 + gid]);
-        }
-        __syncthreads();                                    // T is reused for the staged inverse below
-    }
-    SDB_PI_STAMP(0)
-    for (int j0 = 0; j0 < h; j0 += 4) {
-        const int bjs = j0 >> 3, hi4 = (j0 >> 2) & 1;      // block column / row of the panel, and which half of the block
-        // (1) the panel's four columns of A and four rows of X leave the accumulators
-        if (ra >= bjs && (tig >> 1) == hi4) {
-#pragma unroll
-            for (int bj = 0; bj < 8; ++bj)
-                if (bj == bjs) {
-                    Pn[(tig & 1) * 2 + 0][ra * 8 + gid] = ca[bj][0];
-                    Pn[(tig & 1) * 2 + 1][ra * 8 + gid] = ca[bj][1];
-                }
-        }
-        if (bx == bjs && (gid >> 2) == hi4) {
-#pragma unroll
-            for (int bj = 0; bj < 8; ++bj)
-                if (bj <= bx) {
-                    Xn[gid & 3][bj * 8 + tig * 2 + 0] = cx[bj][0];
-                    Xn[gid & 3][bj * 8 + tig * 2 + 1] = cx[bj][1];
-                }
-        }
-        SDB_PI_STAMP(1)
+    const int nsteps = (h + 3) >> 2;
+    for (int e = tid; e < 4 * PI_S; e += PI_T) (&Xn[0][0])[e] = 0.0;      // columns right of the diagonal block are never written
+
+    if (w >= 8) {
+        // ---------------- panel warps ----------------
         __syncthreads();
-        SDB_PI_STAMP(2)
-        // (2) one warp factors the panel: lane l holds rows l, l + 32 of the panel and columns l, l + 32 of the X rows.
-        // Every lane factors the 4 x 4 pivot block redundantly in registers (broadcast loads, no shuffles): the only
-        // serial chain is four reciprocal square roots.  No masks: rows above the pivot and columns right of it only
-        // ever feed entries that are already final.
-        if (w == 0) {
-            double p[4][2], xq[4][2], g[4][4], rd[4];
+        int bad = 0;
+        for (int s = 0; s < nsteps; ++s) {
+            const int j0 = 4 * s;
+            double (*Lp)[PI_S] = LpB + 4 * (s & 1), (*Xr)[PI_S] = XrB + 4 * (s & 1);
+            pi_bar_sync(2, PI_T);                            // panel s has left the accumulators
+            double v[4][2], g[4][4], rd[4];
+            double (*src)[PI_S] = w == 8 ? Pn : Xn;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) { p[k][e] = Pn[k][lane + 32 * e]; xq[k][e] = Xn[k][lane + 32 * e]; }
+                for (int e = 0; e < 2; ++e) v[k][e] = src[k][lane + 32 * e];
 #pragma unroll
                 for (int i = k; i < 4; ++i) g[i][k] = Pn[k][j0 + i];
             }
-            int bad = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const double d = g[k][k];
@@ -250,51 +209,133 @@ __global__ void __launch_bounds__(256, 1) chol_potrf_inv64_kernel(double *__rest
 #pragma unroll
                     for (int i = k2; i < 4; ++i) g[i][k2] = fma(-g[i][k], g[k2][k], g[i][k2]);
             }
+            // rows of the panel (warp 8) / columns of the X rows (warp 9): the same forward substitution with the 4 x 4 factor.
+            // No masks: rows above the pivot and columns right of it only ever feed entries that are already final.
+            double (*dst)[PI_S] = w == 8 ? Lp : Xr;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                double lk[2], xk[2];
+                double o[2];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) { lk[e] = p[k][e] * rd[k]; xk[e] = xq[k][e] * rd[k]; }   // row j itself: d * rd = L(j, j)
+                for (int e = 0; e < 2; ++e) o[e] = v[k][e] * rd[k];          // row j itself: d * rd = L(j, j)
 #pragma unroll
                 for (int k2 = k + 1; k2 < 4; ++k2)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        p[k2][e] = fma(-lk[e], g[k2][k], p[k2][e]);
-                        xq[k2][e] = fma(-g[k2][k], xk[e], xq[k2][e]);
-                    }
+                    for (int e = 0; e < 2; ++e) v[k2][e] = fma(-o[e], g[k2][k], v[k2][e]);
 #pragma unroll
-                for (int e = 0; e < 2; ++e) { Lp[k][lane + 32 * e] = lk[e]; Xr[k][lane + 32 * e] = xk[e]; }
+                for (int e = 0; e < 2; ++e) dst[k][lane + 32 * e] = o[e];
             }
-            if (bad && lane == 0 && *info == 0) *info = k0 + bad;           // not positive definite (or NaN)
+            pi_bar_arrive(1, PI_T);                          // panel s is factored
         }
-        SDB_PI_STAMP(3)
+        if (w == 8 && bad && lane == 0 && *info == 0) *info = k0 + bad;     // not positive definite (or NaN)
         __syncthreads();
-        {   // the factored panel goes out: L to global memory, the X rows to the staging area (one entry per thread each)
-            const int k = tid >> 6, r = tid & 63, j = j0 + k;
-            if (r >= j && r < h) A[(int64_t)(k0 + j) * ld + k0 + r] = Lp[k][r];
-            Xs[r * PI_XS + j] = r <= j ? Xr[k][r] : 0.0;
-        }
-        // (3) rank-4 updates of what is still live: rows / columns beyond the panel of A, rows beyond it of X
-        if (j0 + 4 < h) {
-            const int bj_lo = (j0 + 4) >> 3, bj_hi = (j0 + 3) >> 3;
-            if (ra >= bj_lo) {
-                const double fa = -Lp[tig][ra * 8 + gid];
+    } else {
+        // ---------------- workers ----------------
+        // block rows: warps w and w + 4 share a scheduler, so their rows pair up as (0,7) (1,6) (2,5) (3,4)
+        const int ra = w < 4 ? w : 11 - w, bx = 7 - ra;
+        double ca[8][2], cx[8][2];
+        if (upd) {
+            double tv[16];
 #pragma unroll
-                for (int bj = 0; bj < 8; ++bj)
-                    if (bj >= bj_lo && bj <= ra) sdb_dmma(ca[bj][0], ca[bj][1], fa, Lp[tig][bj * 8 + gid]);
+            for (int u = 0; u < 16; ++u) {                      // all sixteen loads in flight before the first store
+                const int e = tid + u * 256, i = e & 63, c = e >> 6;
+                tv[u] = i < h ? A[(int64_t)(k0 - 64 + c) * ld + k0 + i] : 0.0;
             }
-            if (bx >= bj_lo) {
-                const double fa = -Lp[tig][bx * 8 + gid];
 #pragma unroll
-                for (int bj = 0; bj < 8; ++bj)
-                    if (bj <= bj_hi && bj <= bx) sdb_dmma(cx[bj][0], cx[bj][1], fa, Xr[tig][bj * 8 + gid]);
+            for (int u = 0; u < 16; ++u) {
+                const int e = tid + u * 256;
+                T[e >> 6][e & 63] = tv[u];
             }
         }
-        SDB_PI_STAMP(4)
+#pragma unroll
+        for (int bj = 0; bj < 8; ++bj)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int i = ra * 8 + gid, c = bj * 8 + tig * 2 + e;
+                ca[bj][e] = (bj <= ra) ? ((i < h && c < h) ? A[(int64_t)(k0 + c) * ld + k0 + i] : (i == c ? 1.0 : 0.0)) : 0.0;
+                cx[bj][e] = (bx * 8 + gid == c) ? 1.0 : 0.0;
+            }
+        __syncthreads();
+        if (upd) {
+#pragma unroll 2
+            for (int kk = 0; kk < 64; kk += 4) {
+                const double fa = -T[kk + tig][ra * 8 + gid];
+#pragma unroll
+                for (int bj = 0; bj < 8; ++bj)
+                    if (bj <= ra) sdb_dmma(ca[bj][0], ca[bj][1], fa, T[kk + tig][bj * 8 + gid]);
+            }
+            pi_bar_sync(3, 256);                                // T is reused for the staged inverse below
+        }
+        SDB_PI_STAMP(0)
+        // hand the four columns of A / rows of X of the panel starting at column jn to the panel warps
+        auto extract = [&](int jn) {
+            const int bjs = jn >> 3, hi4 = (jn >> 2) & 1;       // block column / row of the panel, and which half of the block
+            if (ra >= bjs && (tig >> 1) == hi4) {
+#pragma unroll
+                for (int bj = 0; bj < 8; ++bj)
+                    if (bj == bjs) {
+                        Pn[(tig & 1) * 2 + 0][ra * 8 + gid] = ca[bj][0];
+                        Pn[(tig & 1) * 2 + 1][ra * 8 + gid] = ca[bj][1];
+                    }
+            }
+            if (bx == bjs && (gid >> 2) == hi4) {
+#pragma unroll
+                for (int bj = 0; bj < 8; ++bj)
+                    if (bj <= bx) {
+                        Xn[gid & 3][bj * 8 + tig * 2 + 0] = cx[bj][0];
+                        Xn[gid & 3][bj * 8 + tig * 2 + 1] = cx[bj][1];
+                    }
+            }
+        };
+        extract(0);
+        pi_bar_arrive(2, PI_T);
+        for (int s = 0; s < nsteps; ++s) {
+            const int j0 = 4 * s;
+            double (*Lp)[PI_S] = LpB + 4 * (s & 1), (*Xr)[PI_S] = XrB + 4 * (s & 1);
+            SDB_PI_STAMP(1)
+            pi_bar_sync(1, PI_T);                               // panel s is factored
+            SDB_PI_STAMP(2)
+            const bool more = s + 1 < nsteps;
+            // rank-4 updates of what is still live: rows / columns beyond the panel of A, rows beyond it of X
+            const int bj_lo = (j0 + 4) >> 3, bj_hi = (j0 + 3) >> 3;     // bj_lo is also the block column / row of panel s+1
+            const double fa_a = -Lp[tig][ra * 8 + gid], fa_x = -Lp[tig][bx * 8 + gid];
+            if (more) {
+                // first what panel s+1 needs: block column bj_lo of A and (for its owner) block row bj_lo of X
+                if (ra >= bj_lo) {
+#pragma unroll
+                    for (int bj = 0; bj < 8; ++bj)
+                        if (bj == bj_lo) sdb_dmma(ca[bj][0], ca[bj][1], fa_a, Lp[tig][bj * 8 + gid]);
+                }
+                if (bx == bj_lo) {
+#pragma unroll
+                    for (int bj = 0; bj < 8; ++bj)
+                        if (bj <= bj_hi && bj <= bx) sdb_dmma(cx[bj][0], cx[bj][1], fa_x, Xr[tig][bj * 8 + gid]);
+                }
+                extract(j0 + 4);
+                pi_bar_arrive(2, PI_T);
+                SDB_PI_STAMP(3)
+                // then the rest, while the panel warps are already at work
+                if (ra > bj_lo) {
+#pragma unroll
+                    for (int bj = 0; bj < 8; ++bj)
+                        if (bj > bj_lo && bj <= ra) sdb_dmma(ca[bj][0], ca[bj][1], fa_a, Lp[tig][bj * 8 + gid]);
+                }
+                if (bx > bj_lo) {
+#pragma unroll
+                    for (int bj = 0; bj < 8; ++bj)
+                        if (bj <= bj_hi && bj <= bx) sdb_dmma(cx[bj][0], cx[bj][1], fa_x, Xr[tig][bj * 8 + gid]);
+                }
+            }
+            {   // the factored panel goes out: L to global memory, the X rows to the staging area (one entry per thread each)
+                const int k = tid >> 6, r = tid & 63, j = j0 + k;
+                if (r >= j && r < h) A[(int64_t)(k0 + j) * ld + k0 + r] = Lp[k][r];
+                Xs[r * PI_XS + j] = r <= j ? Xr[k][r] : 0.0;
+            }
+            SDB_PI_STAMP(4)
+        }
+        SDB_PI_PROF_END
+        __syncthreads();
     }
-    SDB_PI_PROF_END
-    __syncthreads();
-    for (int e = tid; e < 64 * 64; e += 256) {
+    for (int e = tid; e < 64 * 64; e += PI_T) {
         const int i = e & 63, c = e >> 6;
         Xout[e] = (i < h && c <= i) ? Xs[c * PI_XS + i] : 0.0;
     }
@@ -391,7 +432,7 @@ __global__ void __launch_bounds__(256) ns_rhs_rows_kernel(const double *__restri
 }
 
 // c = R^{-1} (g1 - B12 y2),  lambda = Q [0; y2]  ->  COEFS [(n + q) x m] row-major.  One CTA per right-hand side.
-__global__ void __launch_bounds__(NS_T, 1) ns_finish_kernel(const double *__restrict__ S, int64_t ld, int n, int q,
+__global__ void __launch_bounds__(NS_T, 2) ns_finish_kernel(const double *__restrict__ S, int64_t ld, int n, int q,
                                                             const double *__restrict__ tau, double *__restrict__ F, int64_t ldf,
                                                             int m, double *__restrict__ COEFS) {
     __shared__ double scratch[32];
@@ -494,7 +535,7 @@ static int ns_enqueue(cudaStream_t st, double *S, int64_t ld, int n, int d, int 
         double *xinv = xinv_all + (int64_t)kp * 4096;
         if (kp >= 2) SDB_CUDA(cudaStreamWaitEvent(st, ev_rest[(kp - 2) & 3], 0));     // issued whenever panel kp exists
         sdb_count_launch();
-        chol_potrf_inv64_kernel<<<1, 256, 0, st>>>(A, ld, k0, h, xinv, d_info, kp > 0 ? 1 : 0 SDB_PI_PROF_PASS);
+        chol_potrf_inv64_kernel<<<1, PI_T, 0, st>>>(A, ld, k0, h, xinv, d_info, kp > 0 ? 1 : 0 SDB_PI_PROF_PASS);
         if (last_next == kp - 1 && kp > 0) SDB_CUDA(cudaStreamWaitEvent(st, ev_next[(kp - 1) & 3], 0));
         double *L21 = A + (int64_t)k0 * ld + k0 + h;
         // L21 = A21 L11^{-T}:  (A21 X^T)(r, j) = sum_k A21(r, k) X(j, k),  X(j, k) = xinv[k*64 + j]

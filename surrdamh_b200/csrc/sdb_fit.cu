@@ -484,6 +484,8 @@ __global__ void __launch_bounds__(1024, 1) thin_remove_kernel(const double *__re
 // The removal loop when everything fits in shared memory -- the normal case (n up to ~8000 points for d = 2).
 // The loop is a chain of reductions over n, so it is bound by INSTRUCTIONS ISSUED per point, and this version is
 // built to issue few of them:
+//   * every thread keeps the nearest-neighbour entries of its own points (tid, tid + 512, ...) in registers; shared
+//     memory only holds the coordinates (70 KB for 4352 points in 2-D: the kernel fits beside a resident chain CTA);
 //   * a removed point is "poisoned" in the CTA's private copy (coordinate 0 := 1e150 -> every distance to it is
 //     ~1e150, finite so that the square root stays on its fast path; nn_dist := +inf), so no scan tests an alive flag;
 //   * D is a template parameter (vector loads, unrolled differences);
@@ -519,8 +521,13 @@ __device__ __forceinline__ void thf_argmin(double &best, int &bidx, thf_red &R, 
     best = __hiloint2double((int)hm, (int)lm);
 }
 
-template <int D>
-__global__ void __launch_bounds__(THF_T, 1) thin_remove_fast_kernel(const double *__restrict__ Xg, int n, int dd, int no_keep,
+#define THF_K 16      // points per thread (registers): n <= THF_T * THF_K
+static_assert(THF_T == 512, "the owner of point i is thread i & 511, slot i >> 9");
+
+// KT: table slots per thread.  The 9-slot instantiation (n <= 4608) is capped at 72 registers so that the CTA fits beside
+// a resident chain CTA (concurrent refit); the 16-slot one takes what it needs.
+template <int D, int KT>
+__global__ void __maxnreg__(KT <= 9 ? 72 : 128) thin_remove_fast_kernel(const double *__restrict__ Xg, int n, int dd, int no_keep,
                                                                     const double *__restrict__ nn_dist_g,
                                                                     const int *__restrict__ nn_idx_g, uint8_t *__restrict__ keep_g) {
     extern __shared__ __align__(16) unsigned char thin_sm[];
@@ -529,17 +536,20 @@ __global__ void __launch_bounds__(THF_T, 1) thin_remove_fast_kernel(const double
     __shared__ int ntodo;
     const int d = D ? D : dd;
     const int tid = threadIdx.x;
-    double *Xs = (double *)thin_sm;
-    double *nn_dist = Xs + (size_t)n * d;
-    int *nn_idx = (int *)(nn_dist + n);
+    double *Xs = (double *)thin_sm;                    // the only per-point array in shared memory: the coordinates
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    for (int e = tid; e < n * d; e += THF_T) Xs[e] = Xg[e];
-    for (int i = tid; i < n; i += THF_T) {
-        const int j = nn_idx_g[i];
-        nn_idx[i] = j;
-        nn_dist[i] = j == INT_MAX ? INF : nn_dist_g[i];
-        keep_g[i] = 1;
+    // nearest-neighbour table of the points tid, tid + THF_T, ... in registers
+    const int kmax = (n + THF_T - 1) / THF_T;
+    double nd[KT];
+    int ni[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        const int i = tid + k * THF_T;
+        ni[k] = i < n ? nn_idx_g[i] : INT_MAX;
+        nd[k] = (i < n && ni[k] != INT_MAX) ? nn_dist_g[i] : INF;
+        if (i < n) keep_g[i] = 1;
     }
+    for (int e = tid; e < n * d; e += THF_T) Xs[e] = Xg[e];
     if (tid == 0) ntodo = 0;
     __syncthreads();
     int buf = 0;
@@ -547,26 +557,39 @@ __global__ void __launch_bounds__(THF_T, 1) thin_remove_fast_kernel(const double
         // global minimum of the nearest-neighbour distances; ties -> smallest row (the first flat arg-min of the reference)
         double best = INF;
         int brow = INT_MAX;
-#pragma unroll 4
-        for (int i = tid; i < n; i += THF_T) {
-            const double di = nn_dist[i];
-            const bool lt = di < best;          // i ascending per thread: the first minimum is kept
-            best = lt ? di : best;
-            brow = lt ? i : brow;
-        }
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+            if (k < kmax) {
+                const bool lt = nd[k] < best;       // index ascending with k: the first minimum is kept
+                best = lt ? nd[k] : best;
+                brow = lt ? tid + k * THF_T : brow;
+            }
         thf_argmin(best, brow, R, buf);
         buf ^= 1;
         const int v = brow;
         if (v == INT_MAX) break;                // fewer than two alive points (uniform)
-        if (tid == 0) { keep_g[v] = 0; Xs[(size_t)v * d] = THF_POISON; nn_dist[v] = INF; nn_idx[v] = INT_MAX; }
+        {
+            const bool owner = tid == (v & (THF_T - 1));
+            if (owner) { keep_g[v] = 0; Xs[(size_t)v * d] = THF_POISON; }
+            const int slot = owner ? (v >> 9) : -1;
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+                nd[k] = k == slot ? INF : nd[k];
+                ni[k] = k == slot ? INT_MAX : ni[k];
+            }
+        }
         // rows whose nearest neighbour was the victim must be rescanned (usually one or two)
+        int pending = 0;                         // bit k: own point k still waits for its rescan (more than 1024 rows at once)
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+            if (k < kmax && ni[k] == v) pending |= 1 << k;
         bool again;
         do {
-#pragma unroll 4
-            for (int i = tid; i < n; i += THF_T)
-                if (nn_idx[i] == v && i != v) {
+#pragma unroll
+            for (int k = 0; k < KT; ++k)
+                if (pending & (1 << k)) {
                     const int slot = atomicAdd(&ntodo, 1);
-                    if (slot < 1024) todo[slot] = i;
+                    if (slot < 1024) { todo[slot] = tid + k * THF_T; pending &= ~(1 << k); }
                 }
             __syncthreads();                     // also publishes the poisoned coordinates of v
             const int found = ntodo;
@@ -604,10 +627,16 @@ __global__ void __launch_bounds__(THF_T, 1) thin_remove_fast_kernel(const double
                 }
                 thf_argmin(b, bj, R, buf);
                 buf ^= 1;
-                if (tid == 0) {                   // only poisoned points left: nobody else is alive
-                    const bool none = !(b < 0.5 * THF_POISON);
-                    nn_dist[row] = none ? INF : b;
-                    nn_idx[row] = none ? INT_MAX : bj;
+                {
+                    const bool none = !(b < 0.5 * THF_POISON);       // only poisoned points left: nobody else is alive
+                    const int slot = tid == (row & (THF_T - 1)) ? (row >> 9) : -1;
+                    const double nb = none ? INF : b;
+                    const int nj = none ? INT_MAX : bj;
+#pragma unroll
+                    for (int k = 0; k < KT; ++k) {
+                        nd[k] = k == slot ? nb : nd[k];
+                        ni[k] = k == slot ? nj : ni[k];
+                    }
                 }
             }
             __syncthreads();
@@ -636,11 +665,15 @@ extern "C" int sdb_rbf_thin(const double *d_X, int64_t n, int32_t d, int64_t no_
     sdb_device_props dp;
     int rc = sdb_get_device_props(&dp);
     if (rc) return rc;
-    const size_t need_fast = (size_t)n * ((size_t)d * 8 + 8 + 4) + 16;
-    if (need_fast + 12288 <= (size_t)dp.smem_optin) {
-        void (*fn)(const double *, int, int, int, const double *, const int *, uint8_t *) =
-            d == 1 ? thin_remove_fast_kernel<1> : d == 2 ? thin_remove_fast_kernel<2> : d == 3 ? thin_remove_fast_kernel<3>
-            : d == 4 ? thin_remove_fast_kernel<4> : thin_remove_fast_kernel<0>;
+    const size_t need_fast = (size_t)n * (size_t)d * 8 + 16;
+    if (n <= THF_T * THF_K && need_fast + 12288 <= (size_t)dp.smem_optin) {
+        void (*fn)(const double *, int, int, int, const double *, const int *, uint8_t *);
+        if (n <= THF_T * 9)
+            fn = d == 1 ? thin_remove_fast_kernel<1, 9> : d == 2 ? thin_remove_fast_kernel<2, 9> : d == 3 ? thin_remove_fast_kernel<3, 9>
+                 : d == 4 ? thin_remove_fast_kernel<4, 9> : thin_remove_fast_kernel<0, 9>;
+        else
+            fn = d == 1 ? thin_remove_fast_kernel<1, THF_K> : d == 2 ? thin_remove_fast_kernel<2, THF_K>
+                 : d == 3 ? thin_remove_fast_kernel<3, THF_K> : d == 4 ? thin_remove_fast_kernel<4, THF_K> : thin_remove_fast_kernel<0, THF_K>;
         SDB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_fast));
         sdb_count_launch();
         fn<<<1, THF_T, need_fast, st>>>(d_X, (int)n, d, (int)no_keep, nn_dist, nn_idx, d_keep);

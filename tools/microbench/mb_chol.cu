@@ -49,12 +49,12 @@ int main() {
     const int reps = 60;
     for (int upd = 0; upd < 2; ++upd) {
         fill_spd<<<1024, 256, 0, st>>>(A, ld, n);
-        float us = time_loop(st, reps, [&](int i) { chol_potrf_inv64_kernel<<<1, 256, 0, st>>>(A, ld, 64 + 64 * (i % 60), 64, xinv + 4096 * (i % 60), info, upd, prof); });
+        float us = time_loop(st, reps, [&](int i) { chol_potrf_inv64_kernel<<<1, PI_T, 0, st>>>(A, ld, 64 + 64 * (i % 60), 64, xinv + 4096 * (i % 60), info, upd, prof); });
         printf("potrf_inv64 upd=%d: %.2f us per launch (back-to-back, includes launch gap)\n", upd, us);
         long long hp[40];
         cudaMemcpy(hp, prof, 8 * 40, cudaMemcpyDeviceToHost);
         for (int w = 0; w < 8; ++w)
-            printf("   warp %d cycles: prologue %lld | extract %lld  barrier %lld  panel(+wait) %lld  barrier+dmma %lld  (sums over 64 columns)\n", w, hp[w * 5], hp[w * 5 + 1],
+            printf("   warp %d cycles: prologue %lld | loop-back %lld  wait-panel %lld  priority+extract %lld  rest+stores %lld  (sums over 64 columns)\n", w, hp[w * 5], hp[w * 5 + 1],
                    hp[w * 5 + 2], hp[w * 5 + 3], hp[w * 5 + 4]);
     }
     {
