@@ -177,6 +177,18 @@ __device__ __forceinline__ sdb_rs sdb_rsqrt_parts(double s) {
     o.q = e * p;
     return o;
 }
+// The same without the guard, for arguments known to be normal numbers (the pair loops start their sum of squares
+// from SDB_R2_FLOOR instead of 0): two ALU instructions fewer per pair in loops whose issue slots are the limit.
+#define SDB_R2_FLOOR 1e-300
+__device__ __forceinline__ sdb_rs sdb_rsqrt_parts_pos(double s) {
+    sdb_rs o;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(o.y0) : "d"(s));
+    o.t = s * o.y0;
+    const double e = fma(-o.t, o.y0, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    o.q = e * p;
+    return o;
+}
 __device__ __forceinline__ double sdb_fast_rsqrt(double s) {
     const sdb_rs r = sdb_rsqrt_parts(s);
     return fma(r.y0, r.q, r.y0);
@@ -203,5 +215,19 @@ __device__ __forceinline__ double sdb_rbf_phi(double s, int kernel_type) {
         case 4: return exp(-s);                                                  // exp(-r^2)
         case 5: return sdb_fast_rsqrt(s + 1.0);                                  // (r^2+1)^(-1/2)
         default: return sdb_fast_sqrt(s);                                        // 0 and 6: r
+    }
+}
+
+// phi for s >= SDB_R2_FLOOR (never zero or subnormal): the pair loops of the RBF surrogate.  A coincident point gives
+// s = 1e-300 instead of 0, i.e. phi = 1e-150 for the linear kernel and 0 (underflow) for the odd powers.
+__device__ __forceinline__ double sdb_rbf_phi_pos(double s, int kernel_type) {
+    switch (kernel_type) {
+        case 1: { const sdb_rs r = sdb_rsqrt_parts_pos(s); const double a = s * r.t; return fma(a, r.q, a); }
+        case 2: { const sdb_rs r = sdb_rsqrt_parts_pos(s); const double a = s * s * r.t; return fma(a, r.q, a); }
+        case 3: { const sdb_rs r = sdb_rsqrt_parts_pos(s); const double a = s * s * s * r.t; return fma(a, r.q, a); }
+        case 7: { const sdb_rs r = sdb_rsqrt_parts_pos(s); const double s2 = s * s; const double a = s2 * s2 * r.t; return fma(a, r.q, a); }
+        case 4: return exp(-s);
+        case 5: return sdb_fast_rsqrt(s + 1.0);
+        default: { const sdb_rs r = sdb_rsqrt_parts_pos(s); return fma(r.t, r.q, r.t); }
     }
 }

@@ -116,14 +116,14 @@ __device__ __forceinline__ void sdb_rbf_partial_kt(const sdb_smodel &s, int d, i
 #pragma unroll 8
     for (int i = first; i < n; i += stride) {
         const double *c = s.centers + (size_t)i * d;
-        double r2 = 0.0;
+        double r2 = SDB_R2_FLOOR;          // keeps the reciprocal square root on normal numbers: no zero / subnormal guard
 #pragma unroll UD
         for (int j = 0; j < DD; ++j)
             if (j < d) {
                 const double df = c[j] - x[j];
                 r2 = fma(df, df, r2);
             }
-        const double phi = sdb_rbf_phi(r2, KT);
+        const double phi = sdb_rbf_phi_pos(r2, KT);
         const double *w = s.coefs + (size_t)i * m;
 #pragma unroll UM
         for (int k = 0; k < MM; ++k)
