@@ -193,10 +193,6 @@ __device__ __forceinline__ double sdb_fast_rsqrt(double s) {
     const sdb_rs r = sdb_rsqrt_parts(s);
     return fma(r.y0, r.q, r.y0);
 }
-__device__ __forceinline__ double sdb_fast_sqrt(double s) {
-    const sdb_rs r = sdb_rsqrt_parts(s);
-    return fma(r.t, r.q, r.t);
-}
 
 __device__ __forceinline__ double sdb_shfl_xor(double v, int lanemask, unsigned mask = 0xffffffffu) {
     return __shfl_xor_sync(mask, v, lanemask);
@@ -205,22 +201,10 @@ __device__ __forceinline__ double sdb_shfl(double v, int src, unsigned mask = 0x
     return __shfl_sync(mask, v, src);
 }
 
-// phi(r) from s = r^2 for the reference's kernel types (surrogate_rbf.py:146-173).
+// phi(r) from s = r^2 for the reference's kernel types (surrogate_rbf.py:146-173), for s >= SDB_R2_FLOOR (never zero or
+// subnormal): the pair loops of the RBF surrogate.  A coincident point gives s = 1e-300 instead of 0, i.e. phi = 1e-150 for
+// the linear kernel and 0 (underflow) for the odd powers.
 __device__ __forceinline__ double sdb_rbf_phi(double s, int kernel_type) {
-    switch (kernel_type) {
-        case 1: { const sdb_rs r = sdb_rsqrt_parts(s); const double a = s * r.t; return fma(a, r.q, a); }            // r^3
-        case 2: { const sdb_rs r = sdb_rsqrt_parts(s); const double a = s * s * r.t; return fma(a, r.q, a); }        // r^5
-        case 3: { const sdb_rs r = sdb_rsqrt_parts(s); const double a = s * s * s * r.t; return fma(a, r.q, a); }    // r^7
-        case 7: { const sdb_rs r = sdb_rsqrt_parts(s); const double s2 = s * s; const double a = s2 * s2 * r.t; return fma(a, r.q, a); }  // r^9
-        case 4: return exp(-s);                                                  // exp(-r^2)
-        case 5: return sdb_fast_rsqrt(s + 1.0);                                  // (r^2+1)^(-1/2)
-        default: return sdb_fast_sqrt(s);                                        // 0 and 6: r
-    }
-}
-
-// phi for s >= SDB_R2_FLOOR (never zero or subnormal): the pair loops of the RBF surrogate.  A coincident point gives
-// s = 1e-300 instead of 0, i.e. phi = 1e-150 for the linear kernel and 0 (underflow) for the odd powers.
-__device__ __forceinline__ double sdb_rbf_phi_pos(double s, int kernel_type) {
     switch (kernel_type) {
         case 1: { const sdb_rs r = sdb_rsqrt_parts_pos(s); const double a = s * r.t; return fma(a, r.q, a); }
         case 2: { const sdb_rs r = sdb_rsqrt_parts_pos(s); const double a = s * s * r.t; return fma(a, r.q, a); }

@@ -123,7 +123,7 @@ __device__ __forceinline__ void sdb_rbf_partial_kt(const sdb_smodel &s, int d, i
                 const double df = c[j] - x[j];
                 r2 = fma(df, df, r2);
             }
-        const double phi = sdb_rbf_phi_pos(r2, KT);
+        const double phi = sdb_rbf_phi(r2, KT);
         const double *w = s.coefs + (size_t)i * m;
 #pragma unroll UM
         for (int k = 0; k < MM; ++k)

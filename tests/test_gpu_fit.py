@@ -179,6 +179,9 @@ def test_thinning_matches_oracle_including_ties(L):
     cases.append((dup, 70))
     cases.append((rs.standard_normal((1500, 4)), 1400))
     cases.append((rs.standard_normal((40, 2)), 1))
+    cases.append((rs.standard_normal((400, 5)), 300))          # dimension without a specialised instantiation
+    cases.append((rs.standard_normal((4700, 2)), 4685))        # more than 9 table slots per thread (16-slot instantiation)
+    cases.append((rs.standard_normal((1000, 32)), 990))        # coordinates do not fit in shared memory: global-memory loop
     for X, keep in cases:
         n, d = X.shape
         want = ORB.greedy_thinning(ORB.pairwise_distance(X, X), keep)
