@@ -105,17 +105,24 @@ __device__ __forceinline__ void sdb_poly_point(const sdb_smodel &s, int d, int m
 // ---------------------------------------------------------------------------------------
 // RBF surrogate (surrogate_rbf.py:20-40): partial sums over centers i = first, first+stride, ...
 // ---------------------------------------------------------------------------------------
-template <int D, int M, int KT>
+// ST: the lane stride when it is 1 or 2 (the plans of the named shapes), 0 = run-time value
+template <int D, int M, int KT, int ST>
 __device__ __forceinline__ void sdb_rbf_partial_kt(const sdb_smodel &s, int d, int m, const double *x, double *acc,
-                                                   int first, int stride) {
+                                                   int first, int stride_rt) {
     constexpr int DD = D ? D : SDB_MAX_D;
     constexpr int UD = D ? D : 1;  // unroll only the specialised sizes
     constexpr int MM = M ? M : SDB_MAX_M;
     constexpr int UM = M ? M : 1;
     const int n = s.n_centers;
+    const int stride = ST ? ST : stride_rt;
+    // running pointers: with a compile-time stride the unrolled body addresses center k of an iteration as pointer +
+    // immediate; indexing by i = first + k * stride costs four ALU instructions per pair, a run-time stride two -- in
+    // a loop whose limit is the issue port (11 FP64 instructions x 2 issue cycles + everything else)
+    const double *c = s.centers + (size_t)first * d;
+    const double *w = s.coefs + (size_t)first * m;
+    const int cs = stride * d, ws = stride * m;
 #pragma unroll 8
-    for (int i = first; i < n; i += stride) {
-        const double *c = s.centers + (size_t)i * d;
+    for (int i = first; i < n; i += stride, c += cs, w += ws) {
         double r2 = SDB_R2_FLOOR;          // keeps the reciprocal square root on normal numbers: no zero / subnormal guard
 #pragma unroll UD
         for (int j = 0; j < DD; ++j)
@@ -124,25 +131,32 @@ __device__ __forceinline__ void sdb_rbf_partial_kt(const sdb_smodel &s, int d, i
                 r2 = fma(df, df, r2);
             }
         const double phi = sdb_rbf_phi(r2, KT);
-        const double *w = s.coefs + (size_t)i * m;
 #pragma unroll UM
         for (int k = 0; k < MM; ++k)
             if (k < m) acc[k] = fma(phi, w[k], acc[k]);
     }
 }
 
+template <int D, int M, int ST>
+__device__ __forceinline__ void sdb_rbf_partial_st(const sdb_smodel &s, int d, int m, const double *x, double *acc,
+                                                   int first, int stride) {
+    switch (s.kernel_type) {
+        case 1: sdb_rbf_partial_kt<D, M, 1, ST>(s, d, m, x, acc, first, stride); break;
+        case 2: sdb_rbf_partial_kt<D, M, 2, ST>(s, d, m, x, acc, first, stride); break;
+        case 3: sdb_rbf_partial_kt<D, M, 3, ST>(s, d, m, x, acc, first, stride); break;
+        case 4: sdb_rbf_partial_kt<D, M, 4, ST>(s, d, m, x, acc, first, stride); break;
+        case 5: sdb_rbf_partial_kt<D, M, 5, ST>(s, d, m, x, acc, first, stride); break;
+        case 7: sdb_rbf_partial_kt<D, M, 7, ST>(s, d, m, x, acc, first, stride); break;
+        default: sdb_rbf_partial_kt<D, M, 0, ST>(s, d, m, x, acc, first, stride); break;
+    }
+}
+
 template <int D, int M>
 __device__ __forceinline__ void sdb_rbf_partial(const sdb_smodel &s, int d, int m, const double *x, double *acc,
                                                 int first, int stride) {
-    switch (s.kernel_type) {
-        case 1: sdb_rbf_partial_kt<D, M, 1>(s, d, m, x, acc, first, stride); break;
-        case 2: sdb_rbf_partial_kt<D, M, 2>(s, d, m, x, acc, first, stride); break;
-        case 3: sdb_rbf_partial_kt<D, M, 3>(s, d, m, x, acc, first, stride); break;
-        case 4: sdb_rbf_partial_kt<D, M, 4>(s, d, m, x, acc, first, stride); break;
-        case 5: sdb_rbf_partial_kt<D, M, 5>(s, d, m, x, acc, first, stride); break;
-        case 7: sdb_rbf_partial_kt<D, M, 7>(s, d, m, x, acc, first, stride); break;
-        default: sdb_rbf_partial_kt<D, M, 0>(s, d, m, x, acc, first, stride); break;
-    }
+    if (stride == 1) sdb_rbf_partial_st<D, M, 1>(s, d, m, x, acc, first, 1);
+    else if (stride == 2) sdb_rbf_partial_st<D, M, 2>(s, d, m, x, acc, first, 2);
+    else sdb_rbf_partial_st<D, M, 0>(s, d, m, x, acc, first, stride);
 }
 
 // linear tail: COEFS[n+d] + sum_j x_j * COEFS[n+j]   (surrogate_rbf.py:38)
