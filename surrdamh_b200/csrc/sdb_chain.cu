@@ -38,7 +38,9 @@ __device__ __forceinline__ void copy_small(void *dst, const void *src, size_t by
     for (size_t i = threadIdx.x; i < (bytes >> 2); i += blockDim.x) ((uint32_t *)dst)[i] = ((const uint32_t *)src)[i];
 }
 
-template <int D, int M>
+// WARP: the call is made by every lane of the warp, converged (the surrogate of a lockstep step) -- the RBF evaluation may
+// then team up neighbouring chains (sdb_rbf_point_split2)
+template <int D, int M, bool WARP = false>
 __device__ __forceinline__ void eval_model_lane(const sdb_smodel &s, int d, int m, const double *x, double *out, int sub,
                                                 int L) {
     // per-lane (or L-lane split) evaluation; used for the surrogate and for cheap truths
@@ -46,7 +48,10 @@ __device__ __forceinline__ void eval_model_lane(const sdb_smodel &s, int d, int 
     constexpr int UM = M ? M : 1;
     switch (s.kind) {
         case SDB_MODEL_POLY: sdb_poly_point<D, M>(s, d, m, x, out); break;
-        case SDB_MODEL_RBF: sdb_rbf_point_split<D, M>(s, d, m, x, out, sub, L); break;
+        case SDB_MODEL_RBF:
+            if (WARP && L <= 16) sdb_rbf_point_split2<D, M>(s, d, m, x, out, L);
+            else sdb_rbf_point_split<D, M>(s, d, m, x, out, sub, L);
+            break;
         case SDB_MODEL_TOY: out[0] = sdb_toy_G(s, x); break;
         default:
 #pragma unroll UM
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, c
     }
     if (damh && (a.phase == SDB_PHASE_PREPARE || a.refresh_pre)) {
         double S[MM];
-        eval_model_lane<D, M>(sur, d, m, u, S, sub, L);
+        eval_model_lane<D, M, true>(sur, d, m, u, S, sub, L);
         pre_u = sdb_log_posterior<D, M>(pr, u, S);
     }
 
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, c
             }
             if (damh) {
                 double S[MM];
-                eval_model_lane<D, M>(sur, d, m, up, S, sub, L);
+                eval_model_lane<D, M, true>(sur, d, m, up, S, sub, L);
                 pre_p = __dadd_rn(sdb_log_likelihood<D, M>(pr, S), lp_p);
                 pass1 = log(uni0) < __dadd_rn(pre_p, -pre_u);
             }

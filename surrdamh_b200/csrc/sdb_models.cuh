@@ -159,6 +159,56 @@ __device__ __forceinline__ void sdb_rbf_partial(const sdb_smodel &s, int d, int 
     else sdb_rbf_partial_st<D, M, 0>(s, d, m, x, acc, first, stride);
 }
 
+// Two points against the same centers: every center / weight load serves two pairs (the loads are two of the ~4.5
+// non-FP64 issue slots a pair costs).  Same per-pair arithmetic as sdb_rbf_partial_kt.
+template <int D, int M, int KT, int ST>
+__device__ __forceinline__ void sdb_rbf_partial2_kt(const sdb_smodel &s, int d, int m, const double *xa, const double *xb,
+                                                    double *acca, double *accb, int first, int stride_rt) {
+    constexpr int DD = D ? D : SDB_MAX_D;
+    constexpr int UD = D ? D : 1;
+    constexpr int MM = M ? M : SDB_MAX_M;
+    constexpr int UM = M ? M : 1;
+    const int n = s.n_centers;
+    const int stride = ST ? ST : stride_rt;
+    const double *c = s.centers + (size_t)first * d;
+    const double *w = s.coefs + (size_t)first * m;
+    const int cs = stride * d, ws = stride * m;
+#pragma unroll 4
+    for (int i = first; i < n; i += stride, c += cs, w += ws) {
+        double ra = SDB_R2_FLOOR, rb = SDB_R2_FLOOR;
+#pragma unroll UD
+        for (int j = 0; j < DD; ++j)
+            if (j < d) {
+                const double cj = c[j];
+                const double da = cj - xa[j], db = cj - xb[j];
+                ra = fma(da, da, ra);
+                rb = fma(db, db, rb);
+            }
+        const double pa = sdb_rbf_phi(ra, KT), pb = sdb_rbf_phi(rb, KT);
+#pragma unroll UM
+        for (int k = 0; k < MM; ++k)
+            if (k < m) {
+                const double wk = w[k];
+                acca[k] = fma(pa, wk, acca[k]);
+                accb[k] = fma(pb, wk, accb[k]);
+            }
+    }
+}
+
+template <int D, int M, int ST>
+__device__ __forceinline__ void sdb_rbf_partial2_st(const sdb_smodel &s, int d, int m, const double *xa, const double *xb,
+                                                    double *acca, double *accb, int first, int stride) {
+    switch (s.kernel_type) {
+        case 1: sdb_rbf_partial2_kt<D, M, 1, ST>(s, d, m, xa, xb, acca, accb, first, stride); break;
+        case 2: sdb_rbf_partial2_kt<D, M, 2, ST>(s, d, m, xa, xb, acca, accb, first, stride); break;
+        case 3: sdb_rbf_partial2_kt<D, M, 3, ST>(s, d, m, xa, xb, acca, accb, first, stride); break;
+        case 4: sdb_rbf_partial2_kt<D, M, 4, ST>(s, d, m, xa, xb, acca, accb, first, stride); break;
+        case 5: sdb_rbf_partial2_kt<D, M, 5, ST>(s, d, m, xa, xb, acca, accb, first, stride); break;
+        case 7: sdb_rbf_partial2_kt<D, M, 7, ST>(s, d, m, xa, xb, acca, accb, first, stride); break;
+        default: sdb_rbf_partial2_kt<D, M, 0, ST>(s, d, m, xa, xb, acca, accb, first, stride); break;
+    }
+}
+
 // linear tail: COEFS[n+d] + sum_j x_j * COEFS[n+j]   (surrogate_rbf.py:38)
 template <int D, int M>
 __device__ __forceinline__ void sdb_rbf_add_tail(const sdb_smodel &s, int d, int m, const double *x, double *acc) {
@@ -189,6 +239,39 @@ __device__ __forceinline__ void sdb_rbf_point_split(const sdb_smodel &s, int d, 
     for (int k = 0; k < MM; ++k)
         if (k < m) out[k] = 0.0;
     sdb_rbf_partial<D, M>(s, d, m, x, out, sub, L);
+    for (int off = L >> 1; off > 0; off >>= 1) {
+#pragma unroll UM
+        for (int k = 0; k < MM; ++k)
+            if (k < m) out[k] += sdb_shfl_xor(out[k], off);
+    }
+    sdb_rbf_add_tail<D, M>(s, d, m, x, out);
+}
+
+// The same for a call every lane of the warp makes (the proposal of every chain in a lockstep step): two neighbouring
+// L-lane groups -- two chains -- form one 2L-lane team; lane t of the team takes centers t, t+2L, ... and evaluates BOTH
+// chains' points against them, then the halves exchange the partial sums that belong to the other chain.  Must be called
+// by the full warp, converged; L <= 16.
+template <int D, int M>
+__device__ __forceinline__ void sdb_rbf_point_split2(const sdb_smodel &s, int d, int m, const double *x, double *out,
+                                                     int L) {
+    constexpr int DD = D ? D : SDB_MAX_D;
+    constexpr int UD = D ? D : 1;
+    constexpr int MM = M ? M : SDB_MAX_M;
+    constexpr int UM = M ? M : 1;
+    const int team = (threadIdx.x & 31) & (2 * L - 1);
+    double xo[DD], other[MM];
+#pragma unroll UD
+    for (int j = 0; j < DD; ++j)
+        if (j < d) xo[j] = sdb_shfl_xor(x[j], L);
+#pragma unroll UM
+    for (int k = 0; k < MM; ++k)
+        if (k < m) { out[k] = 0.0; other[k] = 0.0; }
+    if (L == 1) sdb_rbf_partial2_st<D, M, 2>(s, d, m, x, xo, out, other, team, 2);
+    else if (L == 2) sdb_rbf_partial2_st<D, M, 4>(s, d, m, x, xo, out, other, team, 4);
+    else sdb_rbf_partial2_st<D, M, 0>(s, d, m, x, xo, out, other, team, 2 * L);
+#pragma unroll UM
+    for (int k = 0; k < MM; ++k)
+        if (k < m) out[k] += sdb_shfl_xor(other[k], L);       // the other half's partial sum for MY point
     for (int off = L >> 1; off > 0; off >>= 1) {
 #pragma unroll UM
         for (int k = 0; k < MM; ++k)
