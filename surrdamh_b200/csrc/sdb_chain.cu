@@ -39,7 +39,7 @@ __device__ __forceinline__ void copy_small(void *dst, const void *src, size_t by
 }
 
 // WARP: the call is made by every lane of the warp, converged (the surrogate of a lockstep step) -- the RBF evaluation may
-// then team up neighbouring chains (sdb_rbf_point_split2)
+// then team up neighbouring chains (sdb_rbf_point_team)
 template <int D, int M, bool WARP = false>
 __device__ __forceinline__ void eval_model_lane(const sdb_smodel &s, int d, int m, const double *x, double *out, int sub,
                                                 int L) {
@@ -49,7 +49,8 @@ __device__ __forceinline__ void eval_model_lane(const sdb_smodel &s, int d, int 
     switch (s.kind) {
         case SDB_MODEL_POLY: sdb_poly_point<D, M>(s, d, m, x, out); break;
         case SDB_MODEL_RBF:
-            if (WARP && L <= 16) sdb_rbf_point_split2<D, M>(s, d, m, x, out, L);
+            if (WARP && L <= 8 && D <= 4 && M <= 3 && D && M) sdb_rbf_point_team<D, M, 4>(s, d, m, x, out, L);
+            else if (WARP && L <= 16) sdb_rbf_point_team<D, M, 2>(s, d, m, x, out, L);
             else sdb_rbf_point_split<D, M>(s, d, m, x, out, sub, L);
             break;
         case SDB_MODEL_TOY: out[0] = sdb_toy_G(s, x); break;

@@ -159,11 +159,11 @@ __device__ __forceinline__ void sdb_rbf_partial(const sdb_smodel &s, int d, int 
     else sdb_rbf_partial_st<D, M, 0>(s, d, m, x, acc, first, stride);
 }
 
-// Two points against the same centers: every center / weight load serves two pairs (the loads are two of the ~4.5
-// non-FP64 issue slots a pair costs).  Same per-pair arithmetic as sdb_rbf_partial_kt.
-template <int D, int M, int KT, int ST>
-__device__ __forceinline__ void sdb_rbf_partial2_kt(const sdb_smodel &s, int d, int m, const double *xa, const double *xb,
-                                                    double *acca, double *accb, int first, int stride_rt) {
+// NP points against the same centers: every center / weight load serves NP pairs (the loads are two of the ~4.5
+// non-FP64 issue slots a pair costs).  Same per-pair arithmetic as sdb_rbf_partial_kt.  xs[p][j], acc[p][k].
+template <int D, int M, int KT, int ST, int NP>
+__device__ __forceinline__ void sdb_rbf_partialn_kt(const sdb_smodel &s, int d, int m, const double (*xs)[D ? D : SDB_MAX_D],
+                                                    double (*acc)[M ? M : SDB_MAX_M], int first, int stride_rt) {
     constexpr int DD = D ? D : SDB_MAX_D;
     constexpr int UD = D ? D : 1;
     constexpr int MM = M ? M : SDB_MAX_M;
@@ -173,39 +173,45 @@ __device__ __forceinline__ void sdb_rbf_partial2_kt(const sdb_smodel &s, int d, 
     const double *c = s.centers + (size_t)first * d;
     const double *w = s.coefs + (size_t)first * m;
     const int cs = stride * d, ws = stride * m;
-#pragma unroll 4
+#pragma unroll(8 / NP)
     for (int i = first; i < n; i += stride, c += cs, w += ws) {
-        double ra = SDB_R2_FLOOR, rb = SDB_R2_FLOOR;
+        double r2[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) r2[p] = SDB_R2_FLOOR;
 #pragma unroll UD
         for (int j = 0; j < DD; ++j)
             if (j < d) {
                 const double cj = c[j];
-                const double da = cj - xa[j], db = cj - xb[j];
-                ra = fma(da, da, ra);
-                rb = fma(db, db, rb);
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const double df = cj - xs[p][j];
+                    r2[p] = fma(df, df, r2[p]);
+                }
             }
-        const double pa = sdb_rbf_phi(ra, KT), pb = sdb_rbf_phi(rb, KT);
+        double phi[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) phi[p] = sdb_rbf_phi(r2[p], KT);
 #pragma unroll UM
         for (int k = 0; k < MM; ++k)
             if (k < m) {
                 const double wk = w[k];
-                acca[k] = fma(pa, wk, acca[k]);
-                accb[k] = fma(pb, wk, accb[k]);
+#pragma unroll
+                for (int p = 0; p < NP; ++p) acc[p][k] = fma(phi[p], wk, acc[p][k]);
             }
     }
 }
 
-template <int D, int M, int ST>
-__device__ __forceinline__ void sdb_rbf_partial2_st(const sdb_smodel &s, int d, int m, const double *xa, const double *xb,
-                                                    double *acca, double *accb, int first, int stride) {
+template <int D, int M, int ST, int NP>
+__device__ __forceinline__ void sdb_rbf_partialn_st(const sdb_smodel &s, int d, int m, const double (*xs)[D ? D : SDB_MAX_D],
+                                                    double (*acc)[M ? M : SDB_MAX_M], int first, int stride) {
     switch (s.kernel_type) {
-        case 1: sdb_rbf_partial2_kt<D, M, 1, ST>(s, d, m, xa, xb, acca, accb, first, stride); break;
-        case 2: sdb_rbf_partial2_kt<D, M, 2, ST>(s, d, m, xa, xb, acca, accb, first, stride); break;
-        case 3: sdb_rbf_partial2_kt<D, M, 3, ST>(s, d, m, xa, xb, acca, accb, first, stride); break;
-        case 4: sdb_rbf_partial2_kt<D, M, 4, ST>(s, d, m, xa, xb, acca, accb, first, stride); break;
-        case 5: sdb_rbf_partial2_kt<D, M, 5, ST>(s, d, m, xa, xb, acca, accb, first, stride); break;
-        case 7: sdb_rbf_partial2_kt<D, M, 7, ST>(s, d, m, xa, xb, acca, accb, first, stride); break;
-        default: sdb_rbf_partial2_kt<D, M, 0, ST>(s, d, m, xa, xb, acca, accb, first, stride); break;
+        case 1: sdb_rbf_partialn_kt<D, M, 1, ST, NP>(s, d, m, xs, acc, first, stride); break;
+        case 2: sdb_rbf_partialn_kt<D, M, 2, ST, NP>(s, d, m, xs, acc, first, stride); break;
+        case 3: sdb_rbf_partialn_kt<D, M, 3, ST, NP>(s, d, m, xs, acc, first, stride); break;
+        case 4: sdb_rbf_partialn_kt<D, M, 4, ST, NP>(s, d, m, xs, acc, first, stride); break;
+        case 5: sdb_rbf_partialn_kt<D, M, 5, ST, NP>(s, d, m, xs, acc, first, stride); break;
+        case 7: sdb_rbf_partialn_kt<D, M, 7, ST, NP>(s, d, m, xs, acc, first, stride); break;
+        default: sdb_rbf_partialn_kt<D, M, 0, ST, NP>(s, d, m, xs, acc, first, stride); break;
     }
 }
 
@@ -247,31 +253,38 @@ __device__ __forceinline__ void sdb_rbf_point_split(const sdb_smodel &s, int d, 
     sdb_rbf_add_tail<D, M>(s, d, m, x, out);
 }
 
-// The same for a call every lane of the warp makes (the proposal of every chain in a lockstep step): two neighbouring
-// L-lane groups -- two chains -- form one 2L-lane team; lane t of the team takes centers t, t+2L, ... and evaluates BOTH
-// chains' points against them, then the halves exchange the partial sums that belong to the other chain.  Must be called
-// by the full warp, converged; L <= 16.
-template <int D, int M>
-__device__ __forceinline__ void sdb_rbf_point_split2(const sdb_smodel &s, int d, int m, const double *x, double *out,
-                                                     int L) {
+// The same for a call every lane of the warp makes (the proposal of every chain in a lockstep step): NP neighbouring
+// L-lane groups -- NP chains -- form one team of NP*L lanes; lane t of the team takes centers t, t + NP*L, ... and evaluates
+// ALL the team's points against them (point p of a lane is the one of the group at xor-distance p), then the groups
+// exchange the partial sums that belong to each other.  Must be called by the full warp, converged; NP * L <= 32.
+template <int D, int M, int NP>
+__device__ __forceinline__ void sdb_rbf_point_team(const sdb_smodel &s, int d, int m, const double *x, double *out, int L) {
     constexpr int DD = D ? D : SDB_MAX_D;
     constexpr int UD = D ? D : 1;
     constexpr int MM = M ? M : SDB_MAX_M;
     constexpr int UM = M ? M : 1;
-    const int team = (threadIdx.x & 31) & (2 * L - 1);
-    double xo[DD], other[MM];
+    const int team = (threadIdx.x & 31) & (NP * L - 1);
+    double xs[NP][DD], acc[NP][MM];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
 #pragma unroll UD
-    for (int j = 0; j < DD; ++j)
-        if (j < d) xo[j] = sdb_shfl_xor(x[j], L);
+        for (int j = 0; j < DD; ++j)
+            if (j < d) xs[p][j] = p ? sdb_shfl_xor(x[j], p * L) : x[j];
+#pragma unroll UM
+        for (int k = 0; k < MM; ++k)
+            if (k < m) acc[p][k] = 0.0;
+    }
+    if (NP * L == 2) sdb_rbf_partialn_st<D, M, 2, NP>(s, d, m, xs, acc, team, 2);
+    else if (NP * L == 4) sdb_rbf_partialn_st<D, M, 4, NP>(s, d, m, xs, acc, team, 4);
+    else sdb_rbf_partialn_st<D, M, 0, NP>(s, d, m, xs, acc, team, NP * L);
 #pragma unroll UM
     for (int k = 0; k < MM; ++k)
-        if (k < m) { out[k] = 0.0; other[k] = 0.0; }
-    if (L == 1) sdb_rbf_partial2_st<D, M, 2>(s, d, m, x, xo, out, other, team, 2);
-    else if (L == 2) sdb_rbf_partial2_st<D, M, 4>(s, d, m, x, xo, out, other, team, 4);
-    else sdb_rbf_partial2_st<D, M, 0>(s, d, m, x, xo, out, other, team, 2 * L);
-#pragma unroll UM
-    for (int k = 0; k < MM; ++k)
-        if (k < m) out[k] += sdb_shfl_xor(other[k], L);       // the other half's partial sum for MY point
+        if (k < m) {
+            double t = acc[0][k];
+#pragma unroll
+            for (int p = 1; p < NP; ++p) t += sdb_shfl_xor(acc[p][k], p * L);   // group (mine xor p) holds its partial sum for MY point in slot p
+            out[k] = t;
+        }
     for (int off = L >> 1; off > 0; off >>= 1) {
 #pragma unroll UM
         for (int k = 0; k < MM; ++k)
