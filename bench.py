@@ -436,7 +436,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": {"bound": "fp64-pipe", "achieved": achieved_tf, "peak": fp64_peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / fp64_peak_tf,
-                     "traffic": 120953344 if args.workload == "cfg3" and not args.chains and not args.centers else None,
+                     "traffic": 123539712 if args.workload == "cfg3" and not args.chains and not args.centers else None,
                      "traffic_note": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the ncu --set full capture "
                                      "in profiles/r01_chain_kernel_ncu.md; algorithmic bytes = C*K*25 B trace + state = 1.05e8",
                      "kernel": "chain_kernel<%d,%d>" % (d, m),
