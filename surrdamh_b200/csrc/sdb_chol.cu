@@ -21,6 +21,15 @@
 // registers) when the refit runs concurrently with the next block of chain steps
 #define NS_T 512
 
+__device__ __forceinline__ int ns_ld_acquire_early(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ns_st_release_early(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ double ns_block_sum(double v, double *scratch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -68,16 +77,79 @@ __global__ void __launch_bounds__(NS_T, 2) ns_house_qr_kernel(double *__restrict
         const int ncol = (q - 1 - j) + m;
         for (int cc = warp; cc < ncol; cc += nwarp) {
             double *col = cc < q - 1 - j ? P + (int64_t)(j + 1 + cc) * ldp : F + (int64_t)(cc - (q - 1 - j)) * ldf;
-            double w = 0.0;
-            for (int i = j + 1 + lane; i < n; i += 32) w = fma(x[i], col[i], w);
+            // four independent partial sums / eight loads in flight per lane: one warp walks a whole column, so the loop is
+            // bound by the latency of its loads unless several are outstanding
+            double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+            int i = j + 1 + lane;
+            for (; i + 96 < n; i += 128) {
+                w0 = fma(x[i], col[i], w0);
+                w1 = fma(x[i + 32], col[i + 32], w1);
+                w2 = fma(x[i + 64], col[i + 64], w2);
+                w3 = fma(x[i + 96], col[i + 96], w3);
+            }
+            for (; i < n; i += 32) w0 = fma(x[i], col[i], w0);
+            double w = (w0 + w1) + (w2 + w3);
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(0xffffffffu, w, off);
             w += col[j];                      // v_j(j) = 1
             const double tw = tj * w;
-            for (int i = j + 1 + lane; i < n; i += 32) col[i] = fma(-tw, x[i], col[i]);
+#pragma unroll 4
+            for (int i2 = j + 1 + lane; i2 < n; i2 += 32) col[i2] = fma(-tw, x[i2], col[i2]);
             if (lane == 0) col[j] -= tw;
         }
         __syncthreads();
+    }
+}
+
+// The same factorisation for many reflectors (q > 4), one CTA per column of [P | F], cooperative launch: the CTA of column
+// j generates H_j as soon as H_0..H_{j-1} have been applied to its column and publishes it (release flag); every CTA
+// to the right waits for that flag (acquire) and applies H_j to its own column with all its threads.  One flag
+// hand-over and two short passes over a column per reflector, instead of one warp walking whole columns.
+__global__ void __launch_bounds__(NS_T, 2) ns_house_qr_grid_kernel(double *P, int64_t ldp, int n, int q, double *tau, double *F,
+                                                                   int64_t ldf, int m, int *flag) {
+    __shared__ double scratch[32];
+    __shared__ double s_tau, s_scale, s_beta;
+    const int tid = threadIdx.x, cc = blockIdx.x;
+    double *col = cc < q ? P + (int64_t)cc * ldp : F + (int64_t)(cc - q) * ldf;
+    const int nj = cc < q ? cc : q;                      // reflectors to apply to this column
+    for (int j = 0; j < nj && j < n; ++j) {
+        if (tid == 0)
+            while (ns_ld_acquire_early(flag + j) == 0) { }
+        __syncthreads();
+        const double *x = P + (int64_t)j * ldp;          // v_j below the diagonal, written by the CTA of column j
+        const double tj = __ldcg(tau + j);
+        double w = 0.0;
+        for (int i = j + 1 + tid; i < n; i += NS_T) w = fma(__ldcg(x + i), col[i], w);
+        w = ns_block_sum(w, scratch);
+        w += col[j];                                     // v_j(j) = 1
+        const double tw = tj * w;
+        __syncthreads();                                 // col[j] read by everyone before thread 0 changes it
+        for (int i = j + 1 + tid; i < n; i += NS_T) col[i] = fma(-tw, __ldcg(x + i), col[i]);
+        if (tid == 0) col[j] -= tw;
+        __syncthreads();
+    }
+    if (cc < q && cc < n) {                              // generate H_cc from the updated column
+        const int j = cc;
+        double ss = 0.0;
+        for (int i = j + 1 + tid; i < n; i += NS_T) ss = fma(col[i], col[i], ss);
+        ss = ns_block_sum(ss, scratch);
+        if (tid == 0) {
+            const double alpha = col[j];
+            if (ss == 0.0) { s_tau = 0.0; s_scale = 0.0; s_beta = alpha; }
+            else {
+                const double beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+                s_tau = (beta - alpha) / beta;
+                s_scale = 1.0 / (alpha - beta);
+                s_beta = beta;
+            }
+        }
+        __syncthreads();
+        const double sc = s_scale;
+        for (int i = j + 1 + tid; i < n; i += NS_T) col[i] *= sc;
+        if (tid == 0) { col[j] = s_beta; tau[j] = s_tau; }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) ns_st_release_early(flag + j, 1);
     }
 }
 
@@ -129,6 +201,89 @@ __global__ void __launch_bounds__(256) ns_syr2_kernel(double *__restrict__ Phi, 
             *p = val;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Blocked two-sided application of the q reflectors (compact WY, LAPACK dlarft / dsytrd-style):
+//     Q = H_0 ... H_{q-1} = I - V T V^T,      B = Q^T Phi Q = Phi - V Y^T - Y V^T,
+//     W = Phi V,  M = V^T W,  Y = W T - 1/2 V (T^T M T)
+// i.e. ONE read of Phi (a tall-skinny DMMA GEMM) and ONE read-modify-write (a rank-2q DMMA update) instead of the
+// three sweeps per reflector of the one-at-a-time form: 3 n^2 words of traffic instead of 3 q n^2.
+// ---------------------------------------------------------------------------------------------------
+// explicit V (n x q, unit lower trapezoidal) into both operand panels: VY = [V | Y], YV = [Y | V] (leading dimension n)
+__global__ void __launch_bounds__(256) ns_vmat_kernel(const double *__restrict__ P, int64_t ldp, int n, int q,
+                                                      double *__restrict__ VY, double *__restrict__ YV) {
+    const int64_t total = (int64_t)n * q;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e % n), j = (int)(e / n);
+        const double v = i < j ? 0.0 : (i == j ? 1.0 : P[(int64_t)j * ldp + i]);
+        VY[(int64_t)j * n + i] = v;
+        YV[(int64_t)(q + j) * n + i] = v;
+    }
+}
+
+// T (q x q upper triangular, dlarft forward / columnwise) from tau and G = V^T V, then Z = T^T M T.  One CTA; q <= 33.
+__global__ void __launch_bounds__(256) ns_wy_small_kernel(int q, const double *__restrict__ tau, const double *__restrict__ G,
+                                                          const double *__restrict__ Mq, double *__restrict__ Tout,
+                                                          double *__restrict__ Zout) {
+    __shared__ double T[SDB_MAX_D + 1][SDB_MAX_D + 2], U[SDB_MAX_D + 1][SDB_MAX_D + 2];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < q * q; e += blockDim.x) T[e / q][e % q] = 0.0;
+    __syncthreads();
+    for (int j = 0; j < q; ++j) {
+        // T(0:j, j) = -tau_j T(0:j, 0:j) (V(:, 0:j)^T v_j),  V(:, i)^T v_j = G(i, j)
+        if (tid < j) {
+            double s = 0.0;
+            for (int l = tid; l < j; ++l) s = fma(T[tid][l], G[l * q + j], s);
+            T[tid][j] = -tau[j] * s;
+        }
+        if (tid == j) T[j][j] = tau[j];
+        __syncthreads();
+    }
+    // U = M T,  Z = T^T U
+    for (int e = tid; e < q * q; e += blockDim.x) {
+        const int r = e / q, c = e % q;
+        double s = 0.0;
+        for (int l = 0; l <= c; ++l) s = fma(Mq[r * q + l], T[l][c], s);       // M symmetric: row-major == column-major
+        U[r][c] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < q * q; e += blockDim.x) {
+        const int r = e / q, c = e % q;
+        double s = 0.0;
+        for (int l = 0; l <= r; ++l) s = fma(T[l][r], U[l][c], s);
+        Zout[r * q + c] = s;
+        Tout[r * q + c] = T[r][c];
+    }
+}
+
+// Y = W T - 1/2 V Z  ->  VY[:, q:2q] and YV[:, 0:q].  One thread per (row, column); W, V with leading dimension n.
+__global__ void __launch_bounds__(256) ns_wy_y_kernel(int n, int q, const double *__restrict__ W, const double *__restrict__ T,
+                                                      const double *__restrict__ Z, double *__restrict__ VY,
+                                                      double *__restrict__ YV) {
+    __shared__ double Ts[(SDB_MAX_D + 1) * (SDB_MAX_D + 1)], Zs[(SDB_MAX_D + 1) * (SDB_MAX_D + 1)];
+    for (int e = threadIdx.x; e < q * q; e += blockDim.x) { Ts[e] = T[e]; Zs[e] = Z[e]; }
+    __syncthreads();
+    const int64_t total = (int64_t)n * q;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e % n), c = (int)(e / n);
+        double s = 0.0, t = 0.0;
+        for (int l = 0; l <= c; ++l) s = fma(W[(int64_t)l * n + i], Ts[l * q + c], s);          // T upper triangular
+        for (int l = 0; l < q; ++l) t = fma(VY[(int64_t)l * n + i], Zs[l * q + c], t);
+        const double y = fma(-0.5, t, s);
+        VY[(int64_t)(q + c) * n + i] = y;
+        YV[(int64_t)c * n + i] = y;
+    }
+}
+
+// B22 *= -1 (kernels that are NEGATIVE definite on the null space of P^T)
+__global__ void __launch_bounds__(256) ns_negate_kernel(double *__restrict__ S, int64_t ld, int q, int n) {
+    const int r = q + blockIdx.x * 32 + (threadIdx.x & 31);
+    const int c0 = q + blockIdx.y * 32 + (threadIdx.x >> 5) * 4;
+    if (r >= n) return;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (c0 + k < n) S[(int64_t)(c0 + k) * ld + r] = -S[(int64_t)(c0 + k) * ld + r];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -491,17 +646,64 @@ static int ns_enqueue(cudaStream_t st, double *S, int64_t ld, int n, int d, int 
     const double sgn = (kernel_type == 0 || kernel_type == 6) ? -1.0 : 1.0;
     SDB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
     SDB_CUDA(cudaMemsetAsync(ready, 0, sizeof(int) * (nb / 64 + 1), st));
-    sdb_count_launch();
-    ns_house_qr_kernel<<<1, NS_T, 0, st>>>(P, ld, n, q, tau, F, ld, m);
-    for (int j = 0; j < q; ++j) {
+    if (q <= 4) {
         sdb_count_launch();
-        ns_vec_kernel<<<(n + 255) / 256, 256, 0, st>>>(P, ld, n, j, v);
+        ns_house_qr_kernel<<<1, NS_T, 0, st>>>(P, ld, n, q, tau, F, ld, m);
+    } else {
+        int *qflag = ready + (nb / 64 + 1);
+        SDB_CUDA(cudaMemsetAsync(qflag, 0, sizeof(int) * (SDB_MAX_D + 1), st));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(q + m); cfg.blockDim = dim3(NS_T); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeCooperative; at.val.cooperative = 1;     // the flag waits need every CTA resident
+        cfg.attrs = &at; cfg.numAttrs = 1;
         sdb_count_launch();
-        ns_symv_kernel<<<(n + 7) / 8, 256, 0, st>>>(S, ld, n, v, w);
+        int64_t ld64 = ld;
+        SDB_CUDA(cudaLaunchKernelEx(&cfg, ns_house_qr_grid_kernel, P, ld64, n, q, tau, F, ld64, m, qflag));
+    }
+    if (q <= 4) {
+        // few reflectors (d <= 3): one at a time, three sweeps over the matrix each -- cheaper than the fixed cost of the
+        // blocked form's nine launches
+        for (int j = 0; j < q; ++j) {
+            sdb_count_launch();
+            ns_vec_kernel<<<(n + 255) / 256, 256, 0, st>>>(P, ld, n, j, v);
+            sdb_count_launch();
+            ns_symv_kernel<<<(n + 7) / 8, 256, 0, st>>>(S, ld, n, v, w);
+            sdb_count_launch();
+            ns_z_kernel<<<1, NS_T, 0, st>>>(n, v, w, tau, j, z);
+            sdb_count_launch();
+            ns_syr2_kernel<<<dim3((n + 31) / 32, (n + 31) / 32), 256, 0, st>>>(S, ld, n, v, z, q, j == q - 1 ? sgn : 1.0);
+        }
+    } else {   // B = Q^T Phi Q by the compact-WY form: W = Phi V, M = V^T W, G = V^T V, T, Y, then Phi -= V Y^T + Y V^T
+        double *VY = (double *)(ready + 2 * (nb / 64 + 2) + 2 * ((SDB_MAX_D + 2) / 2 + 1));
+        double *YV = VY + (int64_t)n * 2 * q;
+        double *W = YV + (int64_t)n * 2 * q;
+        double *Gq = W + (int64_t)n * q, *Mq = Gq + q * q, *Tq = Mq + q * q, *Zq = Tq + q * q;
+        double *slab = Zq + q * q;
+        const int tiles_m = (n + GM_BM - 1) / GM_BM;
+        int nslab_w = (296 + tiles_m - 1) / tiles_m;
+        if (nslab_w > 8) nslab_w = 8;
+        int nslab_s = n / 512;
+        if (nslab_s > 64) nslab_s = 64;
+        if (nslab_s < 1) nslab_s = 1;
         sdb_count_launch();
-        ns_z_kernel<<<1, NS_T, 0, st>>>(n, v, w, tau, j, z);
+        ns_vmat_kernel<<<592, 256, 0, st>>>(P, ld, n, q, VY, YV);
+        int rc = sdb_gemm(st, n, q, n, 1.0, S, 1, ld, VY, 1, n, 0.0, W, n, nslab_w, slab);                 // W = Phi V
+        if (rc) return rc;
+        rc = sdb_gemm(st, q, q, n, 1.0, VY, n, 1, W, 1, n, 0.0, Mq, q, nslab_s, slab);                     // M = V^T W
+        if (rc) return rc;
+        rc = sdb_gemm(st, q, q, n, 1.0, VY, n, 1, VY, 1, n, 0.0, Gq, q, nslab_s, slab);                    // G = V^T V
+        if (rc) return rc;
         sdb_count_launch();
-        ns_syr2_kernel<<<dim3((n + 31) / 32, (n + 31) / 32), 256, 0, st>>>(S, ld, n, v, z, q, j == q - 1 ? sgn : 1.0);
+        ns_wy_small_kernel<<<1, 256, 0, st>>>(q, tau, Gq, Mq, Tq, Zq);
+        sdb_count_launch();
+        ns_wy_y_kernel<<<592, 256, 0, st>>>(n, q, W, Tq, Zq, VY, YV);
+        rc = sdb_gemm(st, n, n, 2 * q, -1.0, VY, 1, n, YV, n, 1, 1.0, S, ld);                                // Phi -= V Y^T + Y V^T
+        if (rc) return rc;
+        if (sgn != 1.0) {
+            sdb_count_launch();
+            ns_negate_kernel<<<dim3((nb + 31) / 32, (nb + 31) / 32), 256, 0, st>>>(S, ld, q, n);
+        }
     }
     // Cholesky of B22 = S[q:n, q:n] with the right-hand sides as m extra rows (the forward substitution rides on the
     // panel solve and the trailing update).  Right-looking with a look-ahead of one panel: after the triangular solve
@@ -589,9 +791,10 @@ static int ns_enqueue(cudaStream_t st, double *S, int64_t ld, int n, int d, int 
 }
 
 extern "C" int64_t sdb_rbf_fit_nullspace_work(int64_t n, int32_t d, int32_t m) {
-    const int64_t N = n + d + 1, ld = ns_ld(n, d, m);
-    // system (N columns of ld) | right-hand sides | tau, v, w, z | inverses of the diagonal blocks | block flags
-    return ld * N + ld * m + 3 * n + 128 + (n / 64 + 2) * 4096 + (n / 64 + 2) / 2 + 8;
+    const int64_t N = n + d + 1, ld = ns_ld(n, d, m), q = d + 1;
+    // system (N columns of ld) | right-hand sides | tau, v, w, z | inverses of the diagonal blocks | block flags |
+    // WY panels [V | Y], [Y | V], W | G, M, T, Z | split-K slabs of the tall-skinny products
+    return ld * N + ld * m + 3 * n + 128 + (n / 64 + 2) * 4096 + (n / 64 + 4) + 8 + SDB_MAX_D + 8 + 5 * n * q + 4 * q * q + 8 * n * q + 64 * q * q;
 }
 
 // Same contract as sdb_rbf_fit (X [n x d], Y [n x m] -> d_COEFS [(n+d+1) x m] row-major) for kernel types

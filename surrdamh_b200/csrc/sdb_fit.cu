@@ -301,6 +301,53 @@ __global__ void __launch_bounds__(256) rbf_system_kernel(const double *__restric
         for (int k = 0; k < m; ++k) RHS[(size_t)k * ld + i] = i < n ? Y[(size_t)i * m + k] : 0.0;
 }
 
+// The same for larger d: a 32 x 32 tile of entries per CTA, the 2 x 32 rows of X it needs staged (transposed) in shared
+// memory, every thread a 2 x 2 micro-tile -- per coordinate four loads from shared memory feed four differences instead of
+// eight loads from global memory.  Same per-entry arithmetic and order as rbf_system_kernel.
+__global__ void __launch_bounds__(256) rbf_system_tiled_kernel(const double *__restrict__ X, const double *__restrict__ Y, int n, int d,
+                                                               int m, int kt, double *__restrict__ S, double *__restrict__ RHS,
+                                                               int64_t ld) {
+    __shared__ double Xi[SDB_MAX_D][33], Xj[SDB_MAX_D][33];
+    const int N = n + d + 1;
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    for (int e = tid; e < 32 * d; e += 256) {
+        const int r = e / d, k = e % d;
+        Xi[k][r] = (i0 + r < n) ? X[(size_t)(i0 + r) * d + k] : 0.0;
+        Xj[k][r] = (j0 + r < n) ? X[(size_t)(j0 + r) * d + k] : 0.0;
+    }
+    __syncthreads();
+    double s[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int k = 0; k < d; ++k) {
+        const double a0 = Xi[k][tx], a1 = Xi[k][tx + 16], b0 = Xj[k][ty], b1 = Xj[k][ty + 16];
+        const double d00 = __dadd_rn(b0, -a0), d10 = __dadd_rn(b0, -a1), d01 = __dadd_rn(b1, -a0), d11 = __dadd_rn(b1, -a1);
+        s[0][0] = __dadd_rn(s[0][0], __dmul_rn(d00, d00));
+        s[1][0] = __dadd_rn(s[1][0], __dmul_rn(d10, d10));
+        s[0][1] = __dadd_rn(s[0][1], __dmul_rn(d01, d01));
+        s[1][1] = __dadd_rn(s[1][1], __dmul_rn(d11, d11));
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int i = i0 + tx + 16 * a, j = j0 + ty + 16 * b;
+            if (i < N && j < N) {
+                double v;
+                if (i < n && j < n) v = ref_phi(__dsqrt_rn(s[a][b]), kt);
+                else if (i < n) v = (j - n < d) ? X[(size_t)i * d + (j - n)] : 1.0;
+                else if (j < n) v = (i - n < d) ? X[(size_t)j * d + (i - n)] : 1.0;
+                else v = 0.0;
+                S[(size_t)j * ld + i] = v;
+            }
+        }
+    if (RHS && blockIdx.y == 0 && ty == 0)
+        for (int a = 0; a < 2; ++a) {
+            const int i = i0 + tx + 16 * a;
+            if (i < N)
+                for (int k = 0; k < m; ++k) RHS[(size_t)k * ld + i] = i < n ? Y[(size_t)i * m + k] : 0.0;
+        }
+}
+
 // the system with a leading dimension ld >= n + d + 1 (rows beyond n + d + 1 are left untouched)
 int sdb_rbf_system_ld(const double *d_X, const double *d_Y, int64_t n, int32_t d, int32_t m, int32_t kernel_type, double *d_S,
                       double *d_RHS, int64_t ld, void *stream) {
@@ -310,9 +357,14 @@ int sdb_rbf_system_ld(const double *d_X, const double *d_Y, int64_t n, int32_t d
     SDB_CHECK_ARG(kernel_type >= 0 && kernel_type <= 7, "sdb_rbf_system: kernel_type %d outside [0,7]", kernel_type);
     const int N = (int)n + d + 1;
     SDB_CHECK_ARG(ld >= N, "sdb_rbf_system: leading dimension below n + d + 1");
-    dim3 grid((N + 15) / 16, (N + 15) / 16);
     sdb_count_launch();
-    rbf_system_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_X, d_Y, (int)n, d, m, kernel_type, d_S, d_RHS, ld);
+    if (d > 4) {
+        dim3 grid((N + 31) / 32, (N + 31) / 32);
+        rbf_system_tiled_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_X, d_Y, (int)n, d, m, kernel_type, d_S, d_RHS, ld);
+    } else {
+        dim3 grid((N + 15) / 16, (N + 15) / 16);
+        rbf_system_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_X, d_Y, (int)n, d, m, kernel_type, d_S, d_RHS, ld);
+    }
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
 }

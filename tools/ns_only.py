@@ -1,4 +1,4 @@
-"""Run the null-space fit alone (for ncu launch lists): python tools/ns_only.py [n] [reps]"""
+"""Run the null-space fit alone (for ncu launch lists): python tools/ns_only.py [n] [reps] [d] [m]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -7,7 +7,8 @@ from surrdamh_b200 import _lib as L
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-d, m = 2, 1
+d = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+m = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 rs = np.random.RandomState(0)
 with torch.cuda.stream(torch.cuda.Stream()):
     X = L.dev(rs.standard_normal((n, d)) * 2 + 5)
