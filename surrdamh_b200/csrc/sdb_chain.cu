@@ -668,6 +668,12 @@ static int plan(const sdb_chain_args *a, int *L_out, int *threads_out, int *bloc
     const int blocks_per_sm = (int)((size_t)dp.smem_optin / (smem + 1024)) >= 2 && smem < 100 * 1024 ? 2 : 1;
     const int64_t slots = (int64_t)dp.sm_count * blocks_per_sm;
     int64_t per = (lanes + slots - 1) / slots;
+    if (per > 512) {
+        // several waves of CTAs: size them so that the last wave is as full as the others (131 072 chains on 148 one-CTA
+        // SMs: 293 CTAs of 448 threads in two full waves instead of 256 CTAs of 512 in a full and a 73 % wave)
+        const int64_t waves = (per + 511) / 512;
+        per = (lanes + slots * waves - 1) / (slots * waves);
+    }
     int threads = (int)(((per + 31) / 32) * 32);
     if (threads < 64) threads = 64;
     if (threads > 512) threads = 512;

@@ -729,13 +729,24 @@ static int ns_enqueue(cudaStream_t st, double *S, int64_t ld, int n, int d, int 
     //   diagonal block of panel k+1      -= T1 T1^T         prologue of POTRF+inverse(k+1)           (st)
     //   rest of the columns of panel k+1 -= T[nxt:] T1^T    `nxs`, awaited by the panel solve of k+1
     //   columns of panels >= k+2         -= lower(T' T'^T)  `aux`, awaited by POTRF+inverse(k+2) and by nxs(k+1)
-    int last_rest = -1, last_next = -1;      // last panels whose aux / nxs update was issued
+    // Large matrices (nb >= SDB_CHOL_PAIR_MIN, default 6144): the `aux` update is PAIRED.  After an even panel k only the
+    // 64 columns of panel k+2 receive its contribution (rank 64); everything beyond them waits for the odd panel k+1 and
+    // then receives both contributions in ONE rank-128 pass, which reads and writes each C tile once per 128 columns of L
+    // instead of once per 64 -- the update is bound by that traffic, not by the DMMA pipe.
+    static const int pair_min = getenv("SDB_CHOL_PAIR_MIN") ? atoi(getenv("SDB_CHOL_PAIR_MIN")) : 6144;
+    const bool paired = nb >= pair_min;
+    // trailing matrices of at least this many columns use the 128 x 128 ring kernel (fewer would leave SMs without a tile)
+    static const int big_min = getenv("SDB_CHOL_BIG_MIN") ? atoi(getenv("SDB_CHOL_BIG_MIN")) : 2048;
+    int last_rest = -1, prev_rest = -1, last_next = -1;      // last panels after whose solve an aux / nxs update was issued
     int kp = 0;
     for (int k0 = 0; k0 < nb; k0 += 64, ++kp) {
         const int h = (nb - k0) < 64 ? (nb - k0) : 64;
         const int rest = nb - k0 - h, restx = rest + m;     // rows below the diagonal block, with the right-hand-side rows
         double *xinv = xinv_all + (int64_t)kp * 4096;
-        if (kp >= 2) SDB_CUDA(cudaStreamWaitEvent(st, ev_rest[(kp - 2) & 3], 0));     // issued whenever panel kp exists
+        {   // aux updates issued after the solve of a panel <= kp-2 wrote this panel's columns
+            const int q = (last_rest <= kp - 2) ? last_rest : prev_rest;
+            if (q >= 0) SDB_CUDA(cudaStreamWaitEvent(st, ev_rest[q & 3], 0));
+        }
         sdb_count_launch();
         chol_potrf_inv64_kernel<<<1, PI_T, 0, st>>>(A, ld, k0, h, xinv, d_info, kp > 0 ? 1 : 0 SDB_PI_PROF_PASS);
         if (last_next == kp - 1 && kp > 0) SDB_CUDA(cudaStreamWaitEvent(st, ev_next[(kp - 1) & 3], 0));
@@ -748,16 +759,40 @@ static int ns_enqueue(cudaStream_t st, double *S, int64_t ld, int n, int d, int 
             double *A22 = A + (int64_t)(k0 + h) * ld + k0 + h;
             const int nxt = rest < 64 ? rest : 64;      // columns of the next panel = rows of its diagonal block
             SDB_CUDA(cudaStreamWaitEvent(nxs, ev_trsm[kp & 3], 0));
-            if (last_rest >= 0) SDB_CUDA(cudaStreamWaitEvent(nxs, ev_rest[last_rest & 3], 0));   // aux(kp-1) wrote these columns too
+            if (last_rest >= 0) SDB_CUDA(cudaStreamWaitEvent(nxs, ev_rest[last_rest & 3], 0));   // earlier aux updates wrote these columns too
             rc = sdb_gemm_k64_skinny_update(nxs, restx - nxt, nxt, h, L21 + nxt, L21, A22 + nxt, ld, ld);
             if (rc) return rc;
             SDB_CUDA(cudaEventRecord(ev_next[kp & 3], nxs));
             last_next = kp;
-            if (rest > 64) {
-                SDB_CUDA(cudaStreamWaitEvent(aux, ev_trsm[kp & 3], 0));
-                rc = sdb_syrk_k64_update(aux, restx - 64, rest - 64, h, L21 + 64, L21 + 64, A22 + (int64_t)64 * ld + 64, ld);
-                if (rc) return rc;
+            bool issued = false;
+            if (!paired) {
+                if (rest > 64) {
+                    SDB_CUDA(cudaStreamWaitEvent(aux, ev_trsm[kp & 3], 0));
+                    rc = sdb_syrk_k64_update(aux, restx - 64, rest - 64, h, L21 + 64, L21 + 64, A22 + (int64_t)64 * ld + 64, ld);
+                    if (rc) return rc;
+                    issued = true;
+                }
+            } else if ((kp & 1) == 0) {
+                if (rest > 64) {        // the columns of panel kp+2 only
+                    const int n2 = (rest - 64) < 64 ? (rest - 64) : 64;
+                    SDB_CUDA(cudaStreamWaitEvent(aux, ev_trsm[kp & 3], 0));
+                    rc = sdb_syrk_k64_update(aux, restx - 64, n2, h, L21 + 64, L21 + 64, A22 + (int64_t)64 * ld + 64, ld);
+                    if (rc) return rc;
+                    issued = true;
+                }
+            } else {
+                if (rest > 64) {        // panels kp-1 and kp together: everything beyond panel kp+1
+                    const double *Lp = A + (int64_t)(k0 - 64) * ld + (k0 + 128);      // rows from k0+128, columns k0-64 .. k0+63
+                    SDB_CUDA(cudaStreamWaitEvent(aux, ev_trsm[kp & 3], 0));
+                    if (rest - 64 >= big_min) rc = sdb_syrk_big_update(aux, restx - 64, rest - 64, 64 + h, Lp, Lp, A22 + (int64_t)64 * ld + 64, ld);
+                    else rc = sdb_syrk_k64_update(aux, restx - 64, rest - 64, 64 + h, Lp, Lp, A22 + (int64_t)64 * ld + 64, ld);
+                    if (rc) return rc;
+                    issued = true;
+                }
+            }
+            if (issued) {
                 SDB_CUDA(cudaEventRecord(ev_rest[kp & 3], aux));
+                prev_rest = last_rest;
                 last_rest = kp;
             }
         }

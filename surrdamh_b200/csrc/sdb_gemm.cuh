@@ -178,13 +178,13 @@ static inline int sdb_gemm(cudaStream_t st, int M, int N, int K, double alpha, c
 
 
 // ---------------------------------------------------------------------------------------------------
-// Rank-K update with K <= 64, the LU trailing update:  C[M x N] -= A[M x K] * B[K x N], all column-major
-// with a common leading dimension (A m-contiguous, B k-contiguous).  The whole K extent of a 128 x 64
-// tile is brought into shared memory by cp.async (8-byte pieces: lda may be odd, so 16-byte alignment is
-// not guaranteed) in two halves, so the second half loads while the first is multiplied; no other barrier.
+// Rank-K update (K = 64: the LU trailing update; K = 128: the paired Cholesky update):  C[M x N] -= A[M x K] * B[K x N],
+// all column-major with a common leading dimension (A m-contiguous, B k-contiguous).  The K extent of a 128 x 64
+// tile passes through shared memory by cp.async (8-byte pieces: lda may be odd, so 16-byte alignment is
+// not guaranteed) in slices of 32, two resident, so the next slice loads while the current one is multiplied.
 // ---------------------------------------------------------------------------------------------------
 #define GK_K 64
-#define GK_APAD 8
+#define GK_APAD 4   // As / Bt row stride == 4 (mod 16) doubles: the four k-rows of a fragment load (tig = 0..3) start 8 banks apart
 #define GK_BPAD 4   // Bs is [n][k]: row stride 68 doubles == 4 (mod 16): the 8 n-rows of a fragment load spread over all banks
 
 __device__ __forceinline__ void sdb_cp_async8(void *smem, const void *gmem, bool pred) {
@@ -197,7 +197,8 @@ __device__ __forceinline__ void sdb_cp_async8(void *smem, const void *gmem, bool
 // BT = true : B(k, j) = B[k*ld + j]  (j-contiguous: B = L21^T of the Cholesky SYRK); shared layout Bs[k][n]
 // LOWER: tiles strictly above the diagonal are skipped (symmetric rank-k update of the lower triangle)
 // ASSIGN: C = A B instead of C -= A B (C may alias A when N <= 64: a CTA reads its whole A tile before it stores)
-template <bool BT, bool LOWER, bool ASSIGN>
+// NH: number of 32-wide K slices the kernel is unrolled for (2: K <= 64, 4: K <= 128)
+template <bool BT, bool LOWER, bool ASSIGN, int NH>
 static __global__ void __launch_bounds__(256, 2) sdb_gemm_k64_kernel(const double *__restrict__ A, const double *__restrict__ B,
                                                                      double *__restrict__ C, int64_t ld, int64_t ldb, int M, int N,
                                                                      int K) {
@@ -211,34 +212,39 @@ static __global__ void __launch_bounds__(256, 2) sdb_gemm_k64_kernel(const doubl
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
     const int gid = lane >> 2, tig = lane & 3;
-    // two halves of K: rows [0,32) and [32,64) of As / Bs
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int kb = half * 32;
+    // K is walked in slices of 32: slice h lives in rows [32 (h & 1), 32 (h & 1) + 32) of As / Bs, so two slices are
+    // resident and slice h + 2 is fetched into the rows slice h has just left.  K <= 64 is the one-shot case (both
+    // slices requested up front, no refill); a larger K (the rank-128 update of the Cholesky) re-uses the C tile in the
+    // accumulators, which halves the read-modify-write traffic of C per flop.
+    constexpr int H = NH;
+    auto fetch = [&](int h) {
+        const int kb = (h & 1) * 32, kg = h * 32;       // rows in shared memory / first k of the slice
         // A: 32 k-rows x 128 m  (4096 elements, 16 per thread), m fastest over threads
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
             const int idx = tid + e * 256;
-            const int mm = idx & (GM_BM - 1), kk = kb + (idx >> 7);
-            const bool ok = (m0 + mm < M) && (kk < K);
-            sdb_cp_async8(&As[kk][mm], A + (int64_t)kk * ld + (m0 + mm), ok);
+            const int mm = idx & (GM_BM - 1), kk = idx >> 7;
+            const bool ok = (m0 + mm < M) && (kg + kk < K);
+            sdb_cp_async8(&As[kb + kk][mm], A + (int64_t)(kg + kk) * ld + (m0 + mm), ok);
         }
         // B: 32 k x 64 n (2048 elements, 8 per thread), the memory-contiguous index fastest over threads
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int idx = tid + e * 256;
             if (!BT) {
-                const int kk = kb + (idx & 31), nn = idx >> 5;
-                const bool ok = (n0 + nn < N) && (kk < K);
-                sdb_cp_async8(&Bs[nn][kk], B + (int64_t)(n0 + nn) * ldb + kk, ok);
+                const int kk = idx & 31, nn = idx >> 5;
+                const bool ok = (n0 + nn < N) && (kg + kk < K);
+                sdb_cp_async8(&Bs[nn][kb + kk], B + (int64_t)(n0 + nn) * ldb + (kg + kk), ok);
             } else {
-                const int nn = idx & 63, kk = kb + (idx >> 6);
-                const bool ok = (n0 + nn < N) && (kk < K);
-                sdb_cp_async8(&Bt[kk][nn], B + (int64_t)kk * ldb + (n0 + nn), ok);
+                const int nn = idx & 63, kk = idx >> 6;
+                const bool ok = (n0 + nn < N) && (kg + kk < K);
+                sdb_cp_async8(&Bt[kb + kk][nn], B + (int64_t)(kg + kk) * ldb + (n0 + nn), ok);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-    }
+    };
+    fetch(0);
+    fetch(1);            // beyond K: zero fill (keeps the group count uniform)
     // C - A B is accumulated as (-A) B + C: the C tile is loaded into the accumulators NOW, while the cp.async copies
     // are in flight, so the epilogue is a plain store (no exposed read-modify-write latency at the end)
     double acc[4][4][2];
@@ -252,24 +258,30 @@ static __global__ void __launch_bounds__(256, 2) sdb_gemm_k64_kernel(const doubl
                 acc[i][j][e] = (!ASSIGN && gm < M && gn < N) ? C[(int64_t)gn * ld + gm] : 0.0;
             }
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        if (half == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    for (int h = 0; h < H; ++h) {
+        // groups committed so far: min(h + 2, H); slice h is complete when at most the one after it is pending
+        if (h + 1 < H) asm volatile("cp.async.wait_group 1;" ::: "memory");
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        if (half * 32 < K) {
+        const int kb = (h & 1) * 32;
+        if (h * 32 < K) {
 #pragma unroll
-            for (int ks = 0; ks < 32; ks += 4) {
-                const int k = half * 32 + ks;
-                double fa[4], fb[4];
+        for (int ks = 0; ks < 32; ks += 4) {
+            const int k = kb + ks;
+            double fa[4], fb[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) fa[i] = ASSIGN ? As[k + tig][wm + i * 8 + gid] : -As[k + tig][wm + i * 8 + gid];
+            for (int i = 0; i < 4; ++i) fa[i] = ASSIGN ? As[k + tig][wm + i * 8 + gid] : -As[k + tig][wm + i * 8 + gid];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) fb[j] = BT ? Bt[k + tig][wn + j * 8 + gid] : Bs[wn + j * 8 + gid][k + tig];
+            for (int j = 0; j < 4; ++j) fb[j] = BT ? Bt[k + tig][wn + j * 8 + gid] : Bs[wn + j * 8 + gid][k + tig];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) sdb_dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-            }
+                for (int j = 0; j < 4; ++j) sdb_dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+        }
+        }
+        if (h + 2 < H) {
+            __syncthreads();          // every warp has left slice h
+            fetch(h + 2);
         }
     }
 #pragma unroll
@@ -286,21 +298,30 @@ static __global__ void __launch_bounds__(256, 2) sdb_gemm_k64_kernel(const doubl
             }
 }
 
-template <bool BT, bool LOWER, bool ASSIGN>
-static inline int sdb_gemm_k64_launch(cudaStream_t st, int M, int N, int K, const double *A, const double *B, double *C,
-                                      int64_t ld, int64_t ldb) {
-    if (M <= 0 || N <= 0 || K <= 0) return SDB_OK;
+template <bool BT, bool LOWER, bool ASSIGN, int NH>
+static inline int sdb_gemm_k64_launch_nh(cudaStream_t st, int M, int N, int K, const double *A, const double *B, double *C,
+                                         int64_t ld, int64_t ldb) {
     const int smem = (GK_K * (GM_BM + GK_APAD) + GK_K * (GM_BN + GK_APAD)) * 8;
     static bool attr_set = false;
     if (!attr_set) {
-        SDB_CUDA(cudaFuncSetAttribute((const void *)sdb_gemm_k64_kernel<BT, LOWER, ASSIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SDB_CUDA(cudaFuncSetAttribute((const void *)sdb_gemm_k64_kernel<BT, LOWER, ASSIGN, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     dim3 grid((M + GM_BM - 1) / GM_BM, (N + GM_BN - 1) / GM_BN);
     sdb_count_launch();
-    sdb_gemm_k64_kernel<BT, LOWER, ASSIGN><<<grid, 256, smem, st>>>(A, B, C, ld, ldb, M, N, K);
+    sdb_gemm_k64_kernel<BT, LOWER, ASSIGN, NH><<<grid, 256, smem, st>>>(A, B, C, ld, ldb, M, N, K);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
+}
+
+template <bool BT, bool LOWER, bool ASSIGN>
+static inline int sdb_gemm_k64_launch(cudaStream_t st, int M, int N, int K, const double *A, const double *B, double *C,
+                                      int64_t ld, int64_t ldb) {
+    if (M <= 0 || N <= 0 || K <= 0) return SDB_OK;
+    if (K <= 64) return sdb_gemm_k64_launch_nh<BT, LOWER, ASSIGN, 2>(st, M, N, K, A, B, C, ld, ldb);
+    if (K <= 128) return sdb_gemm_k64_launch_nh<BT, LOWER, ASSIGN, 4>(st, M, N, K, A, B, C, ld, ldb);
+    sdb_set_error("sdb_gemm_k64: K = %d exceeds 128", K);
+    return SDB_ERR_ARG;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -366,6 +387,109 @@ static inline int sdb_gemm_skinny64_launch(cudaStream_t st, int M, int N, int K,
     if (M <= 0 || N <= 0 || K <= 0) return SDB_OK;
     sdb_count_launch();
     sdb_gemm_skinny64_kernel<ASSIGN><<<(M + 31) / 32, 128, 0, st>>>(A, B, C, ld, ldb, M, N, K);
+    SDB_CUDA(cudaGetLastError());
+    return SDB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Symmetric rank-K update of a LARGE trailing matrix (the paired Cholesky update, K = 128):
+//   lower(C[M x N]) -= A[M x K] A2[N x K]^T,   A(i, k) = A[k*ld + i],  A2(j, k) = A2[k*ld + j],  C column-major (ld).
+// The 128 x 64 one-shot kernel above moves 0.16 B through L2 per flop at K = 128 and runs two short-lived CTAs per SM
+// whose load -> multiply -> store phases overlap only with each other (ncu: DMMA sub-pipe active 31 %, top stall long
+// scoreboard).  Here one CTA per SM owns a 128 x 128 tile (warp tile 64 x 32: 32 independent DMMA accumulator chains
+// per warp, 0.09 B per flop), the operands stream through a 5-stage cp.async ring of 16-wide K slices with ONE
+// barrier per slice, and the C tile is loaded straight into the accumulators while the first slices are in flight.
+// ---------------------------------------------------------------------------------------------------
+#define SB_T 128
+#define SB_KS 16
+#define SB_ST 5
+#define SB_LD (SB_T + 4)    // row stride == 4 (mod 16) doubles: conflict-free fragment loads (as GK_APAD)
+
+template <bool LOWER>
+static __global__ void __launch_bounds__(256, 1) sdb_syrk_big_kernel(const double *__restrict__ A, const double *__restrict__ A2,
+                                                                     double *__restrict__ C, int64_t ld, int M, int N, int K) {
+    const int m0 = blockIdx.x * SB_T, n0 = blockIdx.y * SB_T;
+    if (LOWER && n0 > m0 + SB_T - 1) return;
+    extern __shared__ __align__(16) double sb_sm[];
+    typedef double (*slice_t)[SB_LD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int S = (K + SB_KS - 1) / SB_KS;
+    // quarter `part` (0..3) of slice s: the copies of the NEXT slice are issued between the k-steps of the current one, four
+    // per thread at a time -- sixteen back to back fill the load/store queue and stall the warp (ncu: lg_throttle)
+    auto fetch_part = [&](int s, int part) {
+        if (s < S) {
+            slice_t As = (slice_t)(sb_sm + (size_t)(s % SB_ST) * 2 * SB_KS * SB_LD);
+            slice_t Bs = As + SB_KS;
+            const int kg = s * SB_KS;
+#pragma unroll
+            for (int e = 2 * part; e < 2 * part + 2; ++e) {    // 16 k x 128 rows of each operand, 8 + 8 elements per thread
+                const int idx = tid + e * 256, r = idx & (SB_T - 1), kk = idx >> 7;
+                const bool kok = kg + kk < K;
+                sdb_cp_async8(&As[kk][r], A + (int64_t)(kg + kk) * ld + (m0 + r), kok && (m0 + r < M));
+                sdb_cp_async8(&Bs[kk][r], A2 + (int64_t)(kg + kk) * ld + (n0 + r), kok && (n0 + r < N));
+            }
+        }
+        if (part == 3) asm volatile("cp.async.commit_group;" ::: "memory");   // an empty group keeps the count uniform
+    };
+    auto fetch = [&](int s) {
+#pragma unroll
+        for (int part = 0; part < 4; ++part) fetch_part(s, part);
+    };
+#pragma unroll
+    for (int s = 0; s < SB_ST - 1; ++s) fetch(s);
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gm = m0 + wm + i * 8 + gid, gn = n0 + wn + j * 8 + tig * 2 + e;
+                acc[i][j][e] = (gm < M && gn < N) ? C[(int64_t)gn * ld + gm] : 0.0;
+            }
+    for (int s = 0; s < S; ++s) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(SB_ST - 2) : "memory");    // slice s has landed
+        __syncthreads();                                                        // ... for everyone; slice s-1 is free
+        slice_t As = (slice_t)(sb_sm + (size_t)(s % SB_ST) * 2 * SB_KS * SB_LD);
+        slice_t Bs = As + SB_KS;
+#pragma unroll
+        for (int ks = 0; ks < SB_KS; ks += 4) {
+            fetch_part(s + SB_ST - 1, ks >> 2);
+            double fa[8], fb[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) fa[i] = -As[ks + tig][wm + i * 8 + gid];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) fb[j] = Bs[ks + tig][wn + j * 8 + gid];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sdb_dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gm = m0 + wm + i * 8 + gid, gn = n0 + wn + j * 8 + tig * 2 + e;
+                if (gm < M && gn < N) C[(int64_t)gn * ld + gm] = acc[i][j][e];
+            }
+}
+
+static inline int sdb_syrk_big_update(cudaStream_t st, int M, int N, int K, const double *A, const double *A2, double *C, int64_t ld) {
+    if (M <= 0 || N <= 0 || K <= 0) return SDB_OK;
+    const int smem = SB_ST * 2 * SB_KS * SB_LD * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SDB_CUDA(cudaFuncSetAttribute((const void *)sdb_syrk_big_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    dim3 grid((M + SB_T - 1) / SB_T, (N + SB_T - 1) / SB_T);
+    sdb_count_launch();
+    sdb_syrk_big_kernel<true><<<grid, 256, smem, st>>>(A, A2, C, ld, M, N, K);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
 }

@@ -276,6 +276,31 @@ def test_poly_fit_large_well_conditioned(L):
         assert close(M, Mr, rtol=1e-10), (d, m)
 
 
+def test_rbf_nullspace_large_paired_update(L):
+    """n = 6400: above the size where the trailing update of the Cholesky is PAIRED (rank-128 passes through the 128 x 128
+    ring kernel, 64-column look-ahead updates for the even panels; csrc/sdb_chol.cu) -- same solution quality as LAPACK
+    on the same saddle system, evaluation parity on fresh points."""
+    from surrdamh_b200 import surrogate_rbf as SR
+    rs = np.random.RandomState(31)
+    d, m, n, kt = 3, 2, 6400, 1
+    X = rs.standard_normal((n, d))
+    Y = np.stack([np.sin((k + 1) * X).sum(axis=1) for k in range(m)], axis=1)
+    up = SR.Surrogate_update(d, m, kernel_type=kt, solver_type="nullspace")
+    up.add_arrays(X, Y)
+    (CO, Cc), nn = up.update()
+    assert nn == n and getattr(up, "fallbacks", 0) == 0
+    ref = ORB.RbfUpdate(d, m, kernel_type=kt, solver_type="direct")
+    ref.add_arrays(X, Y)
+    (COr, _), _ = ref.update()
+    S, R = ref.last_system, ref.last_rhs
+    res = np.linalg.norm(S @ CO - R) / (np.linalg.norm(S) * np.linalg.norm(CO))
+    res_ref = np.linalg.norm(S @ COr - R) / (np.linalg.norm(S) * np.linalg.norm(COr))
+    assert res <= 20 * res_ref + 1e-16, (res, res_ref)
+    ev = ORB.RbfApply(d, m, kernel_type=kt)
+    pts = np.vstack([X[:100], rs.standard_normal((100, d))])
+    assert close(ev.apply([CO, Cc], pts), ev.apply([COr, Cc], pts), rtol=1e-7)
+
+
 def test_rbf_nullspace_cholesky_matches_direct(L):
     """Additive solver_type 'nullspace' (Householder null-space projection + Cholesky, no pivoting): the same
     solution as the pivoted LU / LAPACK within cond * eps, for every kernel type it accepts, including the
