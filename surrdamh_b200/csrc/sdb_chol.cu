@@ -729,14 +729,14 @@ static int ns_enqueue(cudaStream_t st, double *S, int64_t ld, int n, int d, int 
     //   diagonal block of panel k+1      -= T1 T1^T         prologue of POTRF+inverse(k+1)           (st)
     //   rest of the columns of panel k+1 -= T[nxt:] T1^T    `nxs`, awaited by the panel solve of k+1
     //   columns of panels >= k+2         -= lower(T' T'^T)  `aux`, awaited by POTRF+inverse(k+2) and by nxs(k+1)
-    // Large matrices (nb >= SDB_CHOL_PAIR_MIN, default 6144): the `aux` update is PAIRED.  After an even panel k only the
-    // 64 columns of panel k+2 receive its contribution (rank 64); everything beyond them waits for the odd panel k+1 and
+    // nb >= SDB_CHOL_PAIR_MIN (default 3072; no gain measured below): the `aux` update is PAIRED.  After an even panel k only
+    // the 64 columns of panel k+2 receive its contribution (rank 64); everything beyond them waits for the odd panel k+1 and
     // then receives both contributions in ONE rank-128 pass, which reads and writes each C tile once per 128 columns of L
-    // instead of once per 64 -- the update is bound by that traffic, not by the DMMA pipe.
-    static const int pair_min = getenv("SDB_CHOL_PAIR_MIN") ? atoi(getenv("SDB_CHOL_PAIR_MIN")) : 6144;
+    // instead of once per 64 -- the update is bound by that traffic and by its per-tile prologue, not by the DMMA pipe.
+    static const int pair_min = getenv("SDB_CHOL_PAIR_MIN") ? atoi(getenv("SDB_CHOL_PAIR_MIN")) : 3072;
     const bool paired = nb >= pair_min;
-    // trailing matrices of at least this many columns use the 128 x 128 ring kernel (fewer would leave SMs without a tile)
-    static const int big_min = getenv("SDB_CHOL_BIG_MIN") ? atoi(getenv("SDB_CHOL_BIG_MIN")) : 2048;
+    // trailing matrices of at least this many columns use the TMA-fed 128 x 128 ring kernel (fewer leave SMs without a tile)
+    static const int big_min = getenv("SDB_CHOL_BIG_MIN") ? atoi(getenv("SDB_CHOL_BIG_MIN")) : 1024;
     int last_rest = -1, prev_rest = -1, last_next = -1;      // last panels after whose solve an aux / nxs update was issued
     int kp = 0;
     for (int k0 = 0; k0 < nb; k0 += 64, ++kp) {

@@ -405,30 +405,39 @@ static inline int sdb_gemm_skinny64_launch(cudaStream_t st, int M, int N, int K,
 #define SB_ST 5
 #define SB_LD (SB_T + 4)    // row stride == 4 (mod 16) doubles: conflict-free fragment loads (as GK_APAD)
 
-template <bool LOWER>
-static __global__ void __launch_bounds__(256, 1) sdb_syrk_big_kernel(const double *__restrict__ A, const double *__restrict__ A2,
-                                                                     double *__restrict__ C, int64_t ld, int M, int N, int K) {
-    const int m0 = blockIdx.x * SB_T, n0 = blockIdx.y * SB_T;
+// BN = 128, NT = 256: one CTA per SM;  BN = 64, NT = 128: two CTAs per SM (four warps each, the same 64 x 32 warp tile), so
+// that the C-tile load / store of one CTA overlaps the DMMAs of the other.
+template <bool LOWER, int BN, int NT>
+static __global__ void __launch_bounds__(NT, 256 / NT) sdb_syrk_big_kernel(const double *__restrict__ A, const double *__restrict__ A2,
+                                                                           double *__restrict__ C, int64_t ld, int M, int N, int K) {
+    constexpr int LDB = BN + 4;                                  // == 4 (mod 16) doubles for BN = 64 and 128
+    constexpr int SLICE = SB_KS * (SB_LD + LDB);                 // doubles per ring stage
+    const int m0 = blockIdx.x * SB_T, n0 = blockIdx.y * BN;
     if (LOWER && n0 > m0 + SB_T - 1) return;
     extern __shared__ __align__(16) double sb_sm[];
-    typedef double (*slice_t)[SB_LD];
+    typedef double (*aslice_t)[SB_LD];
+    typedef double (*bslice_t)[LDB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
     const int gid = lane >> 2, tig = lane & 3;
     const int S = (K + SB_KS - 1) / SB_KS;
-    // quarter `part` (0..3) of slice s: the copies of the NEXT slice are issued between the k-steps of the current one, four
-    // per thread at a time -- sixteen back to back fill the load/store queue and stall the warp (ncu: lg_throttle)
+    constexpr int EA = SB_KS * SB_T / NT, EB = SB_KS * BN / NT;  // copies per thread and slice (A: 8 or 16, B: 8)
+    // quarter `part` (0..3) of slice s: the copies of the NEXT slice are issued between the k-steps of the current one --
+    // all of them back to back fill the load/store queue and stall the warp (ncu: lg_throttle)
     auto fetch_part = [&](int s, int part) {
         if (s < S) {
-            slice_t As = (slice_t)(sb_sm + (size_t)(s % SB_ST) * 2 * SB_KS * SB_LD);
-            slice_t Bs = As + SB_KS;
+            aslice_t As = (aslice_t)(sb_sm + (size_t)(s % SB_ST) * SLICE);
+            bslice_t Bs = (bslice_t)(sb_sm + (size_t)(s % SB_ST) * SLICE + SB_KS * SB_LD);
             const int kg = s * SB_KS;
 #pragma unroll
-            for (int e = 2 * part; e < 2 * part + 2; ++e) {    // 16 k x 128 rows of each operand, 8 + 8 elements per thread
-                const int idx = tid + e * 256, r = idx & (SB_T - 1), kk = idx >> 7;
-                const bool kok = kg + kk < K;
-                sdb_cp_async8(&As[kk][r], A + (int64_t)(kg + kk) * ld + (m0 + r), kok && (m0 + r < M));
-                sdb_cp_async8(&Bs[kk][r], A2 + (int64_t)(kg + kk) * ld + (n0 + r), kok && (n0 + r < N));
+            for (int e = part * (EA / 4); e < (part + 1) * (EA / 4); ++e) {
+                const int idx = tid + e * NT, r = idx & (SB_T - 1), kk = idx / SB_T;
+                sdb_cp_async8(&As[kk][r], A + (int64_t)(kg + kk) * ld + (m0 + r), (kg + kk < K) && (m0 + r < M));
+            }
+#pragma unroll
+            for (int e = part * (EB / 4); e < (part + 1) * (EB / 4); ++e) {
+                const int idx = tid + e * NT, r = idx & (BN - 1), kk = idx / BN;
+                sdb_cp_async8(&Bs[kk][r], A2 + (int64_t)(kg + kk) * ld + (n0 + r), (kg + kk < K) && (n0 + r < N));
             }
         }
         if (part == 3) asm volatile("cp.async.commit_group;" ::: "memory");   // an empty group keeps the count uniform
@@ -452,8 +461,8 @@ static __global__ void __launch_bounds__(256, 1) sdb_syrk_big_kernel(const doubl
     for (int s = 0; s < S; ++s) {
         asm volatile("cp.async.wait_group %0;" ::"n"(SB_ST - 2) : "memory");    // slice s has landed
         __syncthreads();                                                        // ... for everyone; slice s-1 is free
-        slice_t As = (slice_t)(sb_sm + (size_t)(s % SB_ST) * 2 * SB_KS * SB_LD);
-        slice_t Bs = As + SB_KS;
+        aslice_t As = (aslice_t)(sb_sm + (size_t)(s % SB_ST) * SLICE);
+        bslice_t Bs = (bslice_t)(sb_sm + (size_t)(s % SB_ST) * SLICE + SB_KS * SB_LD);
 #pragma unroll
         for (int ks = 0; ks < SB_KS; ks += 4) {
             fetch_part(s + SB_ST - 1, ks >> 2);
@@ -479,19 +488,142 @@ static __global__ void __launch_bounds__(256, 1) sdb_syrk_big_kernel(const doubl
             }
 }
 
-static inline int sdb_syrk_big_update(cudaStream_t st, int M, int N, int K, const double *A, const double *A2, double *C, int64_t ld) {
-    if (M <= 0 || N <= 0 || K <= 0) return SDB_OK;
+template <int BN, int NT, int STAGES_UNUSED = 0>
+static inline int sdb_syrk_big_launch(cudaStream_t st, int M, int N, int K, const double *A, const double *A2, double *C, int64_t ld) {
+    const int smem = SB_ST * SB_KS * (SB_LD + BN + 4) * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SDB_CUDA(cudaFuncSetAttribute((const void *)sdb_syrk_big_kernel<true, BN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    dim3 grid((M + SB_T - 1) / SB_T, (N + BN - 1) / BN);
+    sdb_count_launch();
+    sdb_syrk_big_kernel<true, BN, NT><<<grid, NT, smem, st>>>(A, A2, C, ld, M, N, K);
+    SDB_CUDA(cudaGetLastError());
+    return SDB_OK;
+}
+
+// The same 128 x 128 tile fed by TMA: lane l of warp 0 issues ONE 1-D bulk copy (cp.async.bulk + mbarrier transaction count)
+// per k-row of a slice -- 32 copies of 1040 bytes instead of 4096 eight-byte cp.async instructions and their 64-bit address
+// arithmetic, which kept the load/store queue full (ncu: lg_throttle 17 % of the stall samples).  Bulk copies need 16-byte
+// aligned addresses and the saddle matrix has an odd leading dimension, so every row is fetched from the aligned address at
+// or one element below its first element (130 elements: the tile row plus one on either side) and lands with that shift in
+// shared memory; the shift of the row a lane reads, ((address of row 0) / 8 + tig * ld) & 1, is a per-lane constant.
+// PRECONDITION (met by the one caller, the factor inside the Cholesky work buffer): one element before and two after each
+// 128-element row segment of A / A2 are readable; rows beyond M / N may hold anything (they only reach unused accumulators).
+template <bool LOWER>
+static __global__ void __launch_bounds__(256, 1) sdb_syrk_tma_kernel(const double *__restrict__ A, const double *__restrict__ A2,
+                                                                     double *__restrict__ C, int64_t ld, int M, int N, int K) {
+    constexpr int SLICE = 2 * SB_KS * SB_LD;                     // doubles per ring stage (A rows, then A2 rows)
+    constexpr uint32_t ROW_BYTES = (SB_T + 2) * 8;
+    const int m0 = blockIdx.x * SB_T, n0 = blockIdx.y * SB_T;
+    if (LOWER && n0 > m0 + SB_T - 1) return;
+    extern __shared__ __align__(128) double sb_sm[];
+    __shared__ __align__(8) uint64_t full[SB_ST], empty[SB_ST];
+    typedef double (*slice_t)[SB_LD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int S = K / SB_KS;                                     // K is a multiple of 16 (checked by the launcher)
+    const double *Arow = A + m0, *Brow = A2 + n0;
+    const int pa = (int)(((uintptr_t)Arow >> 3) & 1), pb = (int)(((uintptr_t)Brow >> 3) & 1), pl = (int)(ld & 1);
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < SB_ST; ++i) { sdb_mbar_init(&full[i], 1); sdb_mbar_init(&empty[i], 8); }
+        sdb_mbar_fence_init();
+    }
+    __syncthreads();
+    // warp 0 is also the producer: lanes 0..15 fetch the A rows of slice s, lanes 16..31 the A2 rows
+    const int pkk = lane & (SB_KS - 1);
+    const bool pisb = lane >= SB_KS;
+    const double *psrc = (pisb ? Brow : Arow) + (int64_t)pkk * ld - (((pisb ? pb : pa) + pkk * pl) & 1);   // s * 16 * ld is even
+    double *pdst = sb_sm + (size_t)((pisb ? SB_KS : 0) + pkk) * SB_LD;
+    auto issue = [&](int s) {
+        uint64_t *bar = &full[s % SB_ST];
+        if (lane == 0) {
+            sdb_mbar_expect_tx(bar, 2 * SB_KS * ROW_BYTES);
+            sdb_mbar_arrive(bar);
+        }
+        __syncwarp();
+        sdb_bulk_g2s(pdst + (size_t)(s % SB_ST) * SLICE, psrc + (int64_t)s * SB_KS * ld, ROW_BYTES, bar);
+    };
+    if (warp == 0) {
+        for (int s = 0; s < SB_ST - 1 && s < S; ++s) issue(s);
+    }
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gm = m0 + wm + i * 8 + gid, gn = n0 + wn + j * 8 + tig * 2 + e;
+                acc[i][j][e] = (gm < M && gn < N) ? C[(int64_t)gn * ld + gm] : 0.0;
+            }
+    const int ca = wm + gid + ((pa + tig * pl) & 1), cb = wn + gid + ((pb + tig * pl) & 1);    // per-lane column offsets
+    for (int s = 0; s < S; ++s) {
+        if (warp == 0 && s + SB_ST - 1 < S) {
+            // the stage slice s-1 lived in is refilled once all eight warps have left it: per-stage `empty` barriers, no
+            // CTA-wide barrier in the loop (with __syncthreads here the kernel was 15 % slower: ncu barrier stall 14 %)
+            if (s > 0) sdb_mbar_wait(&empty[(s - 1) % SB_ST], (uint32_t)(((s - 1) / SB_ST) & 1));
+            issue(s + SB_ST - 1);
+        }
+        sdb_mbar_wait(&full[s % SB_ST], (uint32_t)((s / SB_ST) & 1));
+        slice_t As = (slice_t)(sb_sm + (size_t)(s % SB_ST) * SLICE);
+        slice_t Bs = As + SB_KS;
+        // fragments of k-step ks+4 are requested before the 32 DMMAs of k-step ks are issued (two register sets)
+        double fa[2][8], fb[2][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fa[0][i] = As[tig][ca + i * 8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fb[0][j] = Bs[tig][cb + j * 8];
+#pragma unroll
+        for (int ks = 0; ks < SB_KS; ks += 4) {
+            const int cur = (ks >> 2) & 1, nxt = cur ^ 1;
+            if (ks + 4 < SB_KS) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) fa[nxt][i] = As[ks + 4 + tig][ca + i * 8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) fb[nxt][j] = Bs[ks + 4 + tig][cb + j * 8];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sdb_dmma(acc[i][j][0], acc[i][j][1], -fa[cur][i], fb[cur][j]);
+        }
+        __syncwarp();
+        if (lane == 0) sdb_mbar_arrive(&empty[s % SB_ST]);      // this warp's loads of slice s have all returned (their values were used)
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gm = m0 + wm + i * 8 + gid, gn = n0 + wn + j * 8 + tig * 2 + e;
+                if (gm < M && gn < N) C[(int64_t)gn * ld + gm] = acc[i][j][e];
+            }
+}
+
+static inline int sdb_syrk_tma_launch(cudaStream_t st, int M, int N, int K, const double *A, const double *A2, double *C, int64_t ld) {
     const int smem = SB_ST * 2 * SB_KS * SB_LD * 8;
     static bool attr_set = false;
     if (!attr_set) {
-        SDB_CUDA(cudaFuncSetAttribute((const void *)sdb_syrk_big_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SDB_CUDA(cudaFuncSetAttribute((const void *)sdb_syrk_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     dim3 grid((M + SB_T - 1) / SB_T, (N + SB_T - 1) / SB_T);
     sdb_count_launch();
-    sdb_syrk_big_kernel<true><<<grid, 256, smem, st>>>(A, A2, C, ld, M, N, K);
+    sdb_syrk_tma_kernel<true><<<grid, 256, smem, st>>>(A, A2, C, ld, M, N, K);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
+}
+
+static inline int sdb_syrk_big_update(cudaStream_t st, int M, int N, int K, const double *A, const double *A2, double *C, int64_t ld) {
+    if (M <= 0 || N <= 0 || K <= 0) return SDB_OK;
+    static const int tma = getenv("SDB_SYRK_TMA") ? atoi(getenv("SDB_SYRK_TMA")) : 1;
+    if (tma && K % SB_KS == 0) return sdb_syrk_tma_launch(st, M, N, K, A, A2, C, ld);
+    return sdb_syrk_big_launch<128, 256>(st, M, N, K, A, A2, C, ld);
 }
 
 // C -= A B, B = U12 (k-contiguous): the LU trailing update
