@@ -392,125 +392,32 @@ static inline int sdb_gemm_skinny64_launch(cudaStream_t st, int M, int N, int K,
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Symmetric rank-K update of a LARGE trailing matrix (the paired Cholesky update, K = 128):
+// Symmetric rank-K update of a LARGE trailing matrix (the paired Cholesky update, K = 128), a TMA-fed DMMA kernel:
 //   lower(C[M x N]) -= A[M x K] A2[N x K]^T,   A(i, k) = A[k*ld + i],  A2(j, k) = A2[k*ld + j],  C column-major (ld).
 // The 128 x 64 one-shot kernel above moves 0.16 B through L2 per flop at K = 128 and runs two short-lived CTAs per SM
 // whose load -> multiply -> store phases overlap only with each other (ncu: DMMA sub-pipe active 31 %, top stall long
-// scoreboard).  Here one CTA per SM owns a 128 x 128 tile (warp tile 64 x 32: 32 independent DMMA accumulator chains
-// per warp, 0.09 B per flop), the operands stream through a 5-stage cp.async ring of 16-wide K slices with ONE
-// barrier per slice, and the C tile is loaded straight into the accumulators while the first slices are in flight.
+// scoreboard).  Here one CTA per SM owns a 128 x 128 tile (8 warps, warp tile 64 x 32: 32 independent DMMA accumulator
+// chains per warp, 0.09 B per flop), the C tile is loaded straight into the accumulators while the first slices are in
+// flight, and the operands stream through a 5-stage ring of 16-wide K slices:
+//  * lane l of warp 0 issues ONE 1-D bulk copy (cp.async.bulk, completion by transaction count on the stage's `full`
+//    mbarrier) per k-row of a slice -- 32 copies of 1040 bytes.  (A first version used 4096 eight-byte cp.async per slice:
+//    their 64-bit address arithmetic and the full load/store queue cost 17 % of the stall samples, lg_throttle.)
+//  * a stage is handed back through its `empty` mbarrier, one arrival per warp; only warp 0 waits on it.  There is no CTA-wide
+//    barrier in the loop (with a __syncthreads per slice the kernel was 15 % slower: barrier stall 14 %).
+//  * the fragments of k-step ks+4 are requested before the 32 DMMAs of k-step ks are issued (two register sets).
+// Bulk copies need 16-byte aligned addresses and the saddle matrix has an odd leading dimension, so every row is fetched
+// from the aligned address at or one element below its first element (130 elements: the tile row plus one on either side)
+// and lands with that shift in shared memory; the shift of the row a lane reads, ((address of row 0) / 8 + tig * ld) & 1,
+// is a per-lane constant.
+// PRECONDITION (met by the one caller, the factor inside the Cholesky work buffer): one element before and two after each
+// 128-element row segment of A / A2 are readable; rows beyond M / N may hold anything (they only reach unused accumulators).
+// Measured: 24.8 TFLOP/s = 0.67 of the FP64 peak on a 15 872^2 update (profiles/r01_syrk_big_ncu.md).
 // ---------------------------------------------------------------------------------------------------
 #define SB_T 128
 #define SB_KS 16
 #define SB_ST 5
-#define SB_LD (SB_T + 4)    // row stride == 4 (mod 16) doubles: conflict-free fragment loads (as GK_APAD)
+#define SB_LD (SB_T + 4)    // row stride == 4 (mod 16) doubles: the k-rows tig = 0..3 of a fragment load start 8 banks apart
 
-// BN = 128, NT = 256: one CTA per SM;  BN = 64, NT = 128: two CTAs per SM (four warps each, the same 64 x 32 warp tile), so
-// that the C-tile load / store of one CTA overlaps the DMMAs of the other.
-template <bool LOWER, int BN, int NT>
-static __global__ void __launch_bounds__(NT, 256 / NT) sdb_syrk_big_kernel(const double *__restrict__ A, const double *__restrict__ A2,
-                                                                           double *__restrict__ C, int64_t ld, int M, int N, int K) {
-    constexpr int LDB = BN + 4;                                  // == 4 (mod 16) doubles for BN = 64 and 128
-    constexpr int SLICE = SB_KS * (SB_LD + LDB);                 // doubles per ring stage
-    const int m0 = blockIdx.x * SB_T, n0 = blockIdx.y * BN;
-    if (LOWER && n0 > m0 + SB_T - 1) return;
-    extern __shared__ __align__(16) double sb_sm[];
-    typedef double (*aslice_t)[SB_LD];
-    typedef double (*bslice_t)[LDB];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
-    const int gid = lane >> 2, tig = lane & 3;
-    const int S = (K + SB_KS - 1) / SB_KS;
-    constexpr int EA = SB_KS * SB_T / NT, EB = SB_KS * BN / NT;  // copies per thread and slice (A: 8 or 16, B: 8)
-    // quarter `part` (0..3) of slice s: the copies of the NEXT slice are issued between the k-steps of the current one --
-    // all of them back to back fill the load/store queue and stall the warp (ncu: lg_throttle)
-    auto fetch_part = [&](int s, int part) {
-        if (s < S) {
-            aslice_t As = (aslice_t)(sb_sm + (size_t)(s % SB_ST) * SLICE);
-            bslice_t Bs = (bslice_t)(sb_sm + (size_t)(s % SB_ST) * SLICE + SB_KS * SB_LD);
-            const int kg = s * SB_KS;
-#pragma unroll
-            for (int e = part * (EA / 4); e < (part + 1) * (EA / 4); ++e) {
-                const int idx = tid + e * NT, r = idx & (SB_T - 1), kk = idx / SB_T;
-                sdb_cp_async8(&As[kk][r], A + (int64_t)(kg + kk) * ld + (m0 + r), (kg + kk < K) && (m0 + r < M));
-            }
-#pragma unroll
-            for (int e = part * (EB / 4); e < (part + 1) * (EB / 4); ++e) {
-                const int idx = tid + e * NT, r = idx & (BN - 1), kk = idx / BN;
-                sdb_cp_async8(&Bs[kk][r], A2 + (int64_t)(kg + kk) * ld + (n0 + r), (kg + kk < K) && (n0 + r < N));
-            }
-        }
-        if (part == 3) asm volatile("cp.async.commit_group;" ::: "memory");   // an empty group keeps the count uniform
-    };
-    auto fetch = [&](int s) {
-#pragma unroll
-        for (int part = 0; part < 4; ++part) fetch_part(s, part);
-    };
-#pragma unroll
-    for (int s = 0; s < SB_ST - 1; ++s) fetch(s);
-    double acc[8][4][2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int gm = m0 + wm + i * 8 + gid, gn = n0 + wn + j * 8 + tig * 2 + e;
-                acc[i][j][e] = (gm < M && gn < N) ? C[(int64_t)gn * ld + gm] : 0.0;
-            }
-    for (int s = 0; s < S; ++s) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(SB_ST - 2) : "memory");    // slice s has landed
-        __syncthreads();                                                        // ... for everyone; slice s-1 is free
-        aslice_t As = (aslice_t)(sb_sm + (size_t)(s % SB_ST) * SLICE);
-        bslice_t Bs = (bslice_t)(sb_sm + (size_t)(s % SB_ST) * SLICE + SB_KS * SB_LD);
-#pragma unroll
-        for (int ks = 0; ks < SB_KS; ks += 4) {
-            fetch_part(s + SB_ST - 1, ks >> 2);
-            double fa[8], fb[4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) fa[i] = -As[ks + tig][wm + i * 8 + gid];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) fb[j] = Bs[ks + tig][wn + j * 8 + gid];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) sdb_dmma(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int gm = m0 + wm + i * 8 + gid, gn = n0 + wn + j * 8 + tig * 2 + e;
-                if (gm < M && gn < N) C[(int64_t)gn * ld + gm] = acc[i][j][e];
-            }
-}
-
-template <int BN, int NT, int STAGES_UNUSED = 0>
-static inline int sdb_syrk_big_launch(cudaStream_t st, int M, int N, int K, const double *A, const double *A2, double *C, int64_t ld) {
-    const int smem = SB_ST * SB_KS * (SB_LD + BN + 4) * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SDB_CUDA(cudaFuncSetAttribute((const void *)sdb_syrk_big_kernel<true, BN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
-    dim3 grid((M + SB_T - 1) / SB_T, (N + BN - 1) / BN);
-    sdb_count_launch();
-    sdb_syrk_big_kernel<true, BN, NT><<<grid, NT, smem, st>>>(A, A2, C, ld, M, N, K);
-    SDB_CUDA(cudaGetLastError());
-    return SDB_OK;
-}
-
-// The same 128 x 128 tile fed by TMA: lane l of warp 0 issues ONE 1-D bulk copy (cp.async.bulk + mbarrier transaction count)
-// per k-row of a slice -- 32 copies of 1040 bytes instead of 4096 eight-byte cp.async instructions and their 64-bit address
-// arithmetic, which kept the load/store queue full (ncu: lg_throttle 17 % of the stall samples).  Bulk copies need 16-byte
-// aligned addresses and the saddle matrix has an odd leading dimension, so every row is fetched from the aligned address at
-// or one element below its first element (130 elements: the tile row plus one on either side) and lands with that shift in
-// shared memory; the shift of the row a lane reads, ((address of row 0) / 8 + tig * ld) & 1, is a per-lane constant.
-// PRECONDITION (met by the one caller, the factor inside the Cholesky work buffer): one element before and two after each
-// 128-element row segment of A / A2 are readable; rows beyond M / N may hold anything (they only reach unused accumulators).
 template <bool LOWER>
 static __global__ void __launch_bounds__(256, 1) sdb_syrk_tma_kernel(const double *__restrict__ A, const double *__restrict__ A2,
                                                                      double *__restrict__ C, int64_t ld, int M, int N, int K) {
@@ -619,11 +526,12 @@ static inline int sdb_syrk_tma_launch(cudaStream_t st, int M, int N, int K, cons
     return SDB_OK;
 }
 
+// lower(C) -= A A2^T for a large trailing matrix, K a multiple of 16 (else, or with SDB_SYRK_TMA=0, the rank-K kernel above)
 static inline int sdb_syrk_big_update(cudaStream_t st, int M, int N, int K, const double *A, const double *A2, double *C, int64_t ld) {
     if (M <= 0 || N <= 0 || K <= 0) return SDB_OK;
     static const int tma = getenv("SDB_SYRK_TMA") ? atoi(getenv("SDB_SYRK_TMA")) : 1;
     if (tma && K % SB_KS == 0) return sdb_syrk_tma_launch(st, M, N, K, A, A2, C, ld);
-    return sdb_syrk_big_launch<128, 256>(st, M, N, K, A, A2, C, ld);
+    return sdb_gemm_k64_launch<true, true, false>(st, M, N, K, A, A2, C, ld, ld);
 }
 
 // C -= A B, B = U12 (k-contiguous): the LU trailing update
