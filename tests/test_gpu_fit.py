@@ -340,3 +340,19 @@ def test_rbf_nullspace_cholesky_matches_direct(L):
         (CO2, C2), n2 = up.update()
         assert n2 == g[f"update{i}_n"][1] and np.array_equal(C2, g[f"update{i}_centers2"])
         assert close(CO2, g[f"update{i}_coefs2"], rtol=1e-5), (i, kt)       # kt 2, 3, 7 take the LU path
+
+
+def test_paired_tma_update_on_ragged_sizes_in_a_subprocess(L):
+    """The paired rank-128 update and its TMA-fed kernel normally start at n = 3072 / 1024 trailing columns.  The thresholds are
+    read once per process, so a child process with SDB_CHOL_PAIR_MIN=0 SDB_CHOL_BIG_MIN=100 re-runs the null-space parity cases
+    (n = 300 .. 2100, d = 1 .. 32, m = 1 .. 5: odd and even leading dimensions, odd and even first rows, partial last tiles and
+    panels) through that path."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, SDB_CHOL_PAIR_MIN="0", SDB_CHOL_BIG_MIN="100")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_fit.py", "-k",
+                        "test_rbf_nullspace_cholesky_matches_direct or test_rbf_nullspace_large_paired_update"],
+                       cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0 and "2 passed" in r.stdout, r.stdout[-2000:]
