@@ -735,6 +735,14 @@ static int ns_enqueue(cudaStream_t st, double *S, int64_t ld, int n, int d, int 
     // instead of once per 64 -- the update is bound by that traffic and by its per-tile prologue, not by the DMMA pipe.
     static const int pair_min = getenv("SDB_CHOL_PAIR_MIN") ? atoi(getenv("SDB_CHOL_PAIR_MIN")) : 3072;
     const bool paired = nb >= pair_min;
+    // group size: G consecutive panels share one rank-64G pass over everything beyond the group (G = 2 is the pairing just
+    // described).  After panel i of a group only the `window` -- the columns of the panels up to the first one of the next
+    // group -- receives its contribution at rank 64; the C tiles of the bulk are read and written once per 64 G columns of L,
+    // and a tile's exposed load / store is amortised over G x 64 k-steps.  Measured (d = 4, m = 3, whole fit, ms):
+    //   n = 4096 (d = 2, m = 1): G = 1 / 2 / 3 -> 2.88 / 2.70 / 2.75, (d = 4, m = 3) 2 / 4 -> 2.96 / 3.07;
+    //   8192: G = 2 / 4 / 8 -> 12.1 / 11.6 / 11.4;  16384: 69.8 / 62.8 / 61.1;  32768: 487 / 427 / 412.
+    static const int group_env = getenv("SDB_CHOL_GROUP") ? atoi(getenv("SDB_CHOL_GROUP")) : 0;
+    const int G = group_env > 1 ? group_env : (nb >= 12288 ? 8 : nb >= 6144 ? 4 : 2);
     // trailing matrices of at least this many columns use the TMA-fed 128 x 128 ring kernel (fewer leave SMs without a tile)
     static const int big_min = getenv("SDB_CHOL_BIG_MIN") ? atoi(getenv("SDB_CHOL_BIG_MIN")) : 1024;
     int last_rest = -1, prev_rest = -1, last_next = -1;      // last panels after whose solve an aux / nxs update was issued
@@ -772,20 +780,21 @@ static int ns_enqueue(cudaStream_t st, double *S, int64_t ld, int n, int d, int 
                     if (rc) return rc;
                     issued = true;
                 }
-            } else if ((kp & 1) == 0) {
-                if (rest > 64) {        // the columns of panel kp+2 only
-                    const int n2 = (rest - 64) < 64 ? (rest - 64) : 64;
+            } else if (kp % G != G - 1) {
+                if (rest > 64) {        // window: the columns of the panels kp+2 .. first panel of the next group
+                    const int nw = 64 * (G - 1 - kp % G), n2 = (rest - 64) < nw ? (rest - 64) : nw;
                     SDB_CUDA(cudaStreamWaitEvent(aux, ev_trsm[kp & 3], 0));
                     rc = sdb_syrk_k64_update(aux, restx - 64, n2, h, L21 + 64, L21 + 64, A22 + (int64_t)64 * ld + 64, ld);
                     if (rc) return rc;
                     issued = true;
                 }
             } else {
-                if (rest > 64) {        // panels kp-1 and kp together: everything beyond panel kp+1
-                    const double *Lp = A + (int64_t)(k0 - 64) * ld + (k0 + 128);      // rows from k0+128, columns k0-64 .. k0+63
+                if (rest > 64) {        // the G panels of the group together: everything beyond panel kp+1
+                    const int kb = 64 * (G - 1);
+                    const double *Lp = A + (int64_t)(k0 - kb) * ld + (k0 + 128);      // rows from k0+128, columns k0-kb .. k0+63
                     SDB_CUDA(cudaStreamWaitEvent(aux, ev_trsm[kp & 3], 0));
-                    if (rest - 64 >= big_min) rc = sdb_syrk_big_update(aux, restx - 64, rest - 64, 64 + h, Lp, Lp, A22 + (int64_t)64 * ld + 64, ld);
-                    else rc = sdb_syrk_k64_update(aux, restx - 64, rest - 64, 64 + h, Lp, Lp, A22 + (int64_t)64 * ld + 64, ld);
+                    if (rest - 64 >= big_min || kb + h > 256) rc = sdb_syrk_big_update(aux, restx - 64, rest - 64, kb + h, Lp, Lp, A22 + (int64_t)64 * ld + 64, ld);
+                    else rc = sdb_syrk_k64_update(aux, restx - 64, rest - 64, kb + h, Lp, Lp, A22 + (int64_t)64 * ld + 64, ld);
                     if (rc) return rc;
                     issued = true;
                 }

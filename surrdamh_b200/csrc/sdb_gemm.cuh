@@ -197,7 +197,7 @@ __device__ __forceinline__ void sdb_cp_async8(void *smem, const void *gmem, bool
 // BT = true : B(k, j) = B[k*ld + j]  (j-contiguous: B = L21^T of the Cholesky SYRK); shared layout Bs[k][n]
 // LOWER: tiles strictly above the diagonal are skipped (symmetric rank-k update of the lower triangle)
 // ASSIGN: C = A B instead of C -= A B (C may alias A when N <= 64: a CTA reads its whole A tile before it stores)
-// NH: number of 32-wide K slices the kernel is unrolled for (2: K <= 64, 4: K <= 128)
+// NH: number of 32-wide K slices the kernel is unrolled for (2: K <= 64, 4: K <= 128, 8: K <= 256)
 template <bool BT, bool LOWER, bool ASSIGN, int NH>
 static __global__ void __launch_bounds__(256, 2) sdb_gemm_k64_kernel(const double *__restrict__ A, const double *__restrict__ B,
                                                                      double *__restrict__ C, int64_t ld, int64_t ldb, int M, int N,
@@ -320,7 +320,8 @@ static inline int sdb_gemm_k64_launch(cudaStream_t st, int M, int N, int K, cons
     if (M <= 0 || N <= 0 || K <= 0) return SDB_OK;
     if (K <= 64) return sdb_gemm_k64_launch_nh<BT, LOWER, ASSIGN, 2>(st, M, N, K, A, B, C, ld, ldb);
     if (K <= 128) return sdb_gemm_k64_launch_nh<BT, LOWER, ASSIGN, 4>(st, M, N, K, A, B, C, ld, ldb);
-    sdb_set_error("sdb_gemm_k64: K = %d exceeds 128", K);
+    if (K <= 256) return sdb_gemm_k64_launch_nh<BT, LOWER, ASSIGN, 8>(st, M, N, K, A, B, C, ld, ldb);
+    sdb_set_error("sdb_gemm_k64: K = %d exceeds 256", K);
     return SDB_ERR_ARG;
 }
 

@@ -342,15 +342,16 @@ def test_rbf_nullspace_cholesky_matches_direct(L):
         assert close(CO2, g[f"update{i}_coefs2"], rtol=1e-5), (i, kt)       # kt 2, 3, 7 take the LU path
 
 
-def test_paired_tma_update_on_ragged_sizes_in_a_subprocess(L):
+@pytest.mark.parametrize("group", ["2", "3", "8"])
+def test_paired_tma_update_on_ragged_sizes_in_a_subprocess(L, group):
     """The paired rank-128 update and its TMA-fed kernel normally start at n = 3072 / 1024 trailing columns.  The thresholds are
     read once per process, so a child process with SDB_CHOL_PAIR_MIN=0 SDB_CHOL_BIG_MIN=100 re-runs the null-space parity cases
     (n = 300 .. 2100, d = 1 .. 32, m = 1 .. 5: odd and even leading dimensions, odd and even first rows, partial last tiles and
-    panels) through that path."""
+    panels) through that path, with groups of 2, 3 and 8 panels per rank-64G pass."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, SDB_CHOL_PAIR_MIN="0", SDB_CHOL_BIG_MIN="100")
+    env = dict(os.environ, SDB_CHOL_PAIR_MIN="0", SDB_CHOL_BIG_MIN="100", SDB_CHOL_GROUP=group)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_fit.py", "-k",
                         "test_rbf_nullspace_cholesky_matches_direct or test_rbf_nullspace_large_paired_update"],
