@@ -306,28 +306,38 @@ __device__ __forceinline__ void sdb_rbf_point_warp(const sdb_smodel &s, int d, i
     constexpr int UM = M ? M : 1;
     const int lane = threadIdx.x & 31;
     unsigned todo = __ballot_sync(0xffffffffu, need && ((lane & (L - 1)) == 0));
+    // two points per pass: every center / weight load serves two pairs (same per-point arithmetic and summation order as one
+    // point per pass, so the results do not depend on how the survivors pair up); a last odd point rides with itself
     while (todo) {
-        const int src = __ffs(todo) - 1;
+        const int src0 = __ffs(todo) - 1;
         todo &= todo - 1;
-        double xs[DD], acc[MM];
+        const int src1 = todo ? __ffs(todo) - 1 : src0;
+        todo &= todo - 1;                       // no-op when todo is already 0
+        double xs[2][DD], acc[2][MM];
 #pragma unroll UD
         for (int j = 0; j < DD; ++j)
-            if (j < d) xs[j] = sdb_shfl(x[j], src);
+            if (j < d) { xs[0][j] = sdb_shfl(x[j], src0); xs[1][j] = sdb_shfl(x[j], src1); }
 #pragma unroll UM
         for (int k = 0; k < MM; ++k)
-            if (k < m) acc[k] = 0.0;
-        sdb_rbf_partial<D, M>(s, d, m, xs, acc, lane, 32);
+            if (k < m) acc[0][k] = acc[1][k] = 0.0;
+        sdb_rbf_partialn_st<D, M, 32, 2>(s, d, m, xs, acc, lane, 32);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
 #pragma unroll UM
             for (int k = 0; k < MM; ++k)
-                if (k < m) acc[k] += sdb_shfl_xor(acc[k], off);
+                if (k < m) { acc[0][k] += sdb_shfl_xor(acc[0][k], off); acc[1][k] += sdb_shfl_xor(acc[1][k], off); }
         }
-        sdb_rbf_add_tail<D, M>(s, d, m, xs, acc);
-        if ((lane / L) == (src / L)) {
+        sdb_rbf_add_tail<D, M>(s, d, m, xs[0], acc[0]);
+        sdb_rbf_add_tail<D, M>(s, d, m, xs[1], acc[1]);
+        if ((lane / L) == (src0 / L)) {
 #pragma unroll UM
             for (int k = 0; k < MM; ++k)
-                if (k < m) out[k] = acc[k];
+                if (k < m) out[k] = acc[0][k];
+        }
+        if (src1 != src0 && (lane / L) == (src1 / L)) {
+#pragma unroll UM
+            for (int k = 0; k < MM; ++k)
+                if (k < m) out[k] = acc[1][k];
         }
     }
 }
