@@ -415,8 +415,14 @@ static inline int sdb_gemm_skinny64_launch(cudaStream_t st, int M, int N, int K,
 // Measured: 24.8 TFLOP/s = 0.67 of the FP64 peak on a 15 872^2 update (profiles/r01_syrk_big_ncu.md).
 // ---------------------------------------------------------------------------------------------------
 #define SB_T 128
+// slice width and ring depth (compile-time; -DSB_KS=32 -DSB_ST=3, the other split of the same shared memory, was 18 % slower
+// at n = 32768: three stages are too shallow a ring)
+#ifndef SB_KS
 #define SB_KS 16
+#endif
+#ifndef SB_ST
 #define SB_ST 5
+#endif
 #define SB_LD (SB_T + 4)    // row stride == 4 (mod 16) doubles: the k-rows tig = 0..3 of a fragment load start 8 banks apart
 
 template <bool LOWER>
@@ -441,11 +447,18 @@ static __global__ void __launch_bounds__(256, 1) sdb_syrk_tma_kernel(const doubl
         sdb_mbar_fence_init();
     }
     __syncthreads();
-    // warp 0 is also the producer: lanes 0..15 fetch the A rows of slice s, lanes 16..31 the A2 rows
-    const int pkk = lane & (SB_KS - 1);
-    const bool pisb = lane >= SB_KS;
-    const double *psrc = (pisb ? Brow : Arow) + (int64_t)pkk * ld - (((pisb ? pb : pa) + pkk * pl) & 1);   // s * 16 * ld is even
-    double *pdst = sb_sm + (size_t)((pisb ? SB_KS : 0) + pkk) * SB_LD;
+    // warp 0 is also the producer: one bulk copy per row of a stage,
+    // row r = lane + 32 c of a stage (c = 0 .. SB_KS/16 - 1): rows 0 .. SB_KS-1 are k-rows of A, the rest k-rows of A2
+    constexpr int PC = 2 * SB_KS / 32;
+    const double *psrc[PC];
+    double *pdst[PC];
+#pragma unroll
+    for (int c = 0; c < PC; ++c) {
+        const int r = lane + 32 * c, pkk = r & (SB_KS - 1);
+        const bool pisb = r >= SB_KS;
+        psrc[c] = (pisb ? Brow : Arow) + (int64_t)pkk * ld - (((pisb ? pb : pa) + pkk * pl) & 1);   // s * SB_KS * ld is even
+        pdst[c] = sb_sm + (size_t)r * SB_LD;
+    }
     auto issue = [&](int s) {
         uint64_t *bar = &full[s % SB_ST];
         if (lane == 0) {
@@ -453,7 +466,9 @@ static __global__ void __launch_bounds__(256, 1) sdb_syrk_tma_kernel(const doubl
             sdb_mbar_arrive(bar);
         }
         __syncwarp();
-        sdb_bulk_g2s(pdst + (size_t)(s % SB_ST) * SLICE, psrc + (int64_t)s * SB_KS * ld, ROW_BYTES, bar);
+#pragma unroll
+        for (int c = 0; c < PC; ++c)
+            sdb_bulk_g2s(pdst[c] + (size_t)(s % SB_ST) * SLICE, psrc[c] + (int64_t)s * SB_KS * ld, ROW_BYTES, bar);
     };
     if (warp == 0) {
         for (int s = 0; s < SB_ST - 1 && s < S; ++s) issue(s);
