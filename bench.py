@@ -4,21 +4,27 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg5]
 
 Workload (default cfg3, BASELINE.json configs[2], the configuration the metric and its 1e9 steps/s
-target are quoted on; it fits one GPU): per GPU 65536 lockstep DAMH chains, d=2, m=1, the
-simple.json Gaussian problem, cubic RBF surrogate with 4096 centers, analytic toy G on the device,
-surrogate_is_updated=true: every 64 lockstep steps the new snapshots are compacted, all-gathered
-(NCCL), at most 256 of them enter the collector's refit (greedy thinning back to 4096 centers,
-saddle-point system build, dense direct solve: null-space projection + Cholesky, `--solver direct` selects
-the LU with partial pivoting that mirrors the reference's solver_type 'direct'), the new coefficients
-are broadcast and every chain switches to them.  Weak scaling: every GPU carries 65536 chains.
+target are quoted on; it fits one GPU): 65536 lockstep DAMH chains, d=2, m=1, the simple.json
+Gaussian problem, cubic RBF surrogate with 4096 centers, analytic toy G on the device,
+surrogate_is_updated=true: every 64 lockstep steps each rank picks its share of 256 new snapshots
+(evenly spaced over the block), ONE NCCL all-gather makes the set common, the collector refits
+(greedy thinning back to 4096 centers, saddle-point system build, dense direct solve: null-space
+projection + Cholesky; `--solver direct` selects the LU with partial pivoting that mirrors the
+reference's solver_type 'direct'), ONE broadcast of the packed state hands the new surrogate to
+every rank.  The headline is WEAK scaling (65536 chains per GPU); with N > 1 the same line carries
+the STRONG-scaling record (65536 chains split evenly over the N GPUs) under "strong".
     cfg2: 4096 chains, frozen polynomial surrogate (degree 5)        (BASELINE.json configs[1])
     cfg5: 131072 chains/GPU, d=4, m=3, frozen cubic RBF 500 centers, frozen 2000-center RBF as G
-One bench "step" = one block of 64 lockstep steps of all chains (+ the refit round in cfg3).
+One bench "step" = one block of 64 lockstep steps of all chains (+ the collector round in cfg3).
 
 One JSON line on stdout (rank 0).  `value` = chain steps/s over all GPUs with state resident in
-HBM; `e2e` = the same through host buffers (pinned H2D of the chain samples, D2H of samples +
-counters every step); `roofline` = the fused chain kernel against the measured FP64 FMA peak;
-`cpu_baseline` = the numpy oracle (reference restatement) on the host cores, frozen surrogate.
+HBM; `e2e` = the same through host buffers: pinned H2D of the chain samples at the start of every
+block, D2H of what a user gets back per block (final samples, counters, the per-chain running
+moments of the chain, the accept / reject trace); `roofline` = the fused chain kernel against the
+measured FP64 FMA peak; `roofline_refit` = the collector round's dense solve (n^3/3 flop) against
+the same peak; `cpu_baseline` = the REFERENCE's own Algorithm_DAMH.run (unmodified modules from
+oracle/_ref, CSV output on) on the host cores -- the numpy oracle when that copy is absent;
+`other_workloads` (N = 1) = short cfg2 / cfg5 records.  NCCL's INFO log goes to stderr.
 """
 import argparse
 import json
@@ -42,13 +48,25 @@ DARCY = dict(prior_mean=0.0, prior_std=1.0, noise_std=[0.2, 0.1, 0.1], no_observ
 WORKLOADS = {
     "cfg3": dict(d=2, m=1, problem=SIMPLE, chains=65536, surrogate="rbf", centers=4096, kernel_type=1, updated=True,
                  block=64, snapshots_per_refit=256, proposal_std=1.0, truth="toy", solver_type="nullspace",
-                 name="illustrative-shape DAMH: 65536 chains/GPU, cubic RBF 4096 centers, surrogate_is_updated, refit every 64 steps"),
+                 name="illustrative-shape DAMH: 65536 chains, cubic RBF 4096 centers, surrogate_is_updated, refit every 64 steps"),
     "cfg2": dict(d=2, m=1, problem=SIMPLE, chains=4096, surrogate="poly", degree=5, updated=False, block=64,
                  proposal_std=1.0, truth="toy", name="simple.json-shape DAMH: 4096 chains, frozen poly degree 5"),
     "cfg5": dict(d=4, m=3, problem=DARCY, chains=131072, surrogate="rbf", centers=500, kernel_type=1, updated=False,
                  block=64, proposal_std=0.2, truth="rbf", truth_centers=2000,
                  name="Darcy-shape surrogate-only DAMH: 131072 chains/GPU, frozen cubic RBF 500 centers, 2000-center RBF as G"),
 }
+METRIC = "surrogate-evaluated DAMH chain steps/s"
+
+
+def static_config(wname, w):
+    """The workload description both arms print verbatim (nothing measured in it)."""
+    return {"workload": "%s: %s" % (wname, w["name"]), "chains_per_gpu": w["chains"], "lockstep_steps_per_bench_step": w["block"],
+            "no_parameters": w["d"], "no_observations": w["m"], "surrogate": w["surrogate"], "centers": w.get("centers"),
+            "poly_degree": w.get("degree"), "surrogate_is_updated": bool(w["updated"]),
+            "refit_every": w["block"] if w["updated"] else None,
+            "snapshots_per_refit": w.get("snapshots_per_refit") if w["updated"] else None,
+            "proposal_std": w["proposal_std"], "true_model": w["truth"],
+            "l2": "GPU arm: 256 MiB flush write before every bench step, inside the timed region"}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -78,9 +96,93 @@ def training_set(w, n, seed):
 
 
 # ----------------------------------------------------------------------------------------------------
-# CPU baseline: the numpy oracle's DAMH chain (restatement of classes_SAMPLER.py / surrogate_*.py)
+# CPU arm: the reference's own classes (oracle/_ref via oracle.ref_import) or, without them, the numpy oracle
 # ----------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
+def reference_available():
+    from oracle import ref_import
+    return ref_import.available()
+
+
+class _Snap:
+    def __init__(self, sample, G_sample, weight=1):
+        self.sample, self.G_sample, self.weight = sample, G_sample, weight
+
+
+def _ref_worker(args):
+    """One host process = one reference sampler: Algorithm_DAMH.run (classes_SAMPLER.py:165-220) with in-process proxies
+    (no MPI hop: favours the reference), CSV output on as process_SAMPLER.py:66-85 configures it."""
+    wname, SOL, truth_SOL, seconds, seed = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    import contextlib
+    import io
+    import warnings
+    from oracle import ref_import as R
+    ns = R.load()
+    w = WORKLOADS[wname]
+    d, m = w["d"], w["m"]
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if w["surrogate"] == "rbf":
+            apply_o = ns.rbf.Surrogate_apply(d, m, kernel_type=w["kernel_type"])
+        else:
+            apply_o = ns.poly.Surrogate_apply(d, m)
+
+        class SurrogateProxy:               # the local-collector proxy of classes_communication.py:83-157, frozen between swaps
+            queue = []
+
+            def send_parameters(self, p):
+                self.p = p.copy()
+
+            def recv_observations(self):
+                return apply_o.apply(SOL, self.p)
+
+            def send_to_data_collector(self, s):
+                self.queue.append(s)
+                if len(self.queue) > 4096:
+                    self.queue.clear()
+
+        if w["truth"] == "toy":
+            solver = ns.solvers.Solver_linela2exp_local()
+        else:
+            t_apply = ns.rbf.Surrogate_apply(d, m, kernel_type=1)
+
+            class solver:                   # noqa: N801  (the frozen truth surrogate behind the solver interface)
+                @staticmethod
+                def set_parameters(p):
+                    solver.p = np.array(p)
+
+                @staticmethod
+                def get_observations():
+                    return t_apply.apply(truth_SOL, solver.p)[0, :]
+
+        class SolverProxy:
+            def send_parameters(self, p):
+                solver.set_parameters(p)
+
+            def recv_observations(self):
+                return solver.get_observations()
+
+        cwd = os.getcwd()
+        tmp = tempfile.mkdtemp(prefix="sdb_ref_")
+        os.chdir(tmp)
+        try:
+            prob = ns.cS.Problem_Gauss(d, saved_samples_name="bench", **w["problem"])
+            prop = ns.cS.Proposal_GaussRandomWalk(d, proposal_std=w["proposal_std"], seed=seed + 1)
+            alg = ns.cS.Algorithm_DAMH(prob, prop, SolverProxy(), Surrogate=SurrogateProxy(), surrogate_is_updated=bool(w["updated"]),
+                                       max_samples=10 ** 9, time_limit=seconds, save_raw_data=True, name="alg000DAMH_rank%d" % seed,
+                                       seed=seed + 2)
+            t0 = time.perf_counter()
+            alg.run()
+            dt = time.perf_counter() - t0
+        finally:
+            os.chdir(cwd)
+            import shutil
+            shutil.rmtree(tmp, ignore_errors=True)
+    return alg.no_accepted + alg.no_rejected + alg.no_prerejected, dt
+
+
+def _port_worker(args):
     wname, SOL, truth_SOL, seconds, seed = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
@@ -91,10 +193,7 @@ def _cpu_worker(args):
     from oracle import surrogate_rbf as ORB
     w = WORKLOADS[wname]
     d, m = w["d"], w["m"]
-    if w["surrogate"] == "rbf":
-        apply_o = ORB.RbfApply(d, m, kernel_type=w["kernel_type"])
-    else:
-        apply_o = OP.PolyApply(d, m)
+    apply_o = ORB.RbfApply(d, m, kernel_type=w["kernel_type"]) if w["surrogate"] == "rbf" else OP.PolyApply(d, m)
 
     class Frozen:
         def send_parameters(self, p):
@@ -122,18 +221,60 @@ def _cpu_worker(args):
     return steps, time.perf_counter() - t0
 
 
-def cpu_baseline(wname, SOL, truth_SOL, seconds, cores=None):
+def cpu_arm(wname, SOL, truth_SOL, seconds, cores=None):
+    """All host cores, one sampler process each, `seconds` of DAMH steps: aggregate chain steps/s."""
     cores = cores or len(os.sched_getaffinity(0))
+    ref = reference_available()
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(wname, SOL, truth_SOL, seconds, 1000 * r) for r in range(cores)])
+        res = pool.map(_ref_worker if ref else _port_worker, [(wname, SOL, truth_SOL, seconds, 1000 * r) for r in range(cores)])
         wall = time.perf_counter() - t0
     steps = sum(r[0] for r in res)
     busy = max(r[1] for r in res)
-    return dict(value=steps / busy, unit="chain steps/s", cores=cores, kind="port",
-                sample="%d processes x %.0f s of oracle DAMH steps (frozen surrogate, in-process proxies, no MPI hop), %d steps"
-                       % (cores, seconds, steps), wall_s=wall)
+    what = ("the reference's Algorithm_DAMH.run (unmodified modules, oracle/_ref), CSV output on, in-process proxies (no MPI hop), "
+            "surrogate frozen between collector swaps") if ref else "numpy oracle DAMH steps (frozen surrogate, in-process proxies, no MPI hop)"
+    return dict(value=steps / busy, unit="chain steps/s", cores=cores, kind="reference" if ref else "port",
+                sample="%d processes x %.0f s of %s; %d steps" % (cores, seconds, what, steps), wall_s=wall)
+
+
+def cpu_models(w):
+    """The surrogate (and cfg5's frozen truth) the CPU samplers evaluate, fitted on the host by the same CPU implementation."""
+    d, m = w["d"], w["m"]
+    if reference_available():
+        import contextlib
+        import io
+        import warnings
+        from oracle import ref_import as R
+        ns = R.load()
+
+        def fit(kind, X, Y, **kw):
+            with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                up = (ns.rbf if kind == "rbf" else ns.poly).Surrogate_update(d, m, **kw)
+                up.add_data([_Snap(X[i], Y[i]) for i in range(X.shape[0])])
+                return up.update()[0]
+    else:
+        from oracle import surrogate_poly as OP
+        from oracle import surrogate_rbf as ORB
+
+        def fit(kind, X, Y, **kw):
+            up = (ORB.RbfUpdate if kind == "rbf" else OP.PolyUpdate)(d, m, **kw)
+            up.add_arrays(X, Y)
+            return up.update()[0]
+    t0 = time.perf_counter()
+    if w["surrogate"] == "rbf":
+        X, Y = training_set(w, w["centers"], 1)
+        SOL = fit("rbf", X, Y, kernel_type=w["kernel_type"], solver_type="direct")
+    else:
+        X, Y = training_set(w, 2000, 1)
+        SOL = fit("poly", X, Y, max_degree=w["degree"])
+    fit_s = time.perf_counter() - t0
+    truth_SOL = None
+    if w["truth"] == "rbf":
+        Xt, Yt = training_set(w, w["truth_centers"], 2)
+        truth_SOL = fit("rbf", Xt, Yt, kernel_type=1, solver_type="direct")
+    return SOL, truth_SOL, fit_s
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -179,33 +320,248 @@ def clocks_summary(path, gpu_index, t0=None, t1=None):
 
 
 # ----------------------------------------------------------------------------------------------------
-def build_models(w, rank_seed=0):
+def build_models(w):
     """Initial surrogate (GPU refit of a synthetic training set) and, for cfg5, the frozen truth."""
     from surrdamh_b200 import surrogate_poly as SP
     from surrdamh_b200 import surrogate_rbf as SR
     from surrdamh_b200.device import DeviceModel
     d, m = w["d"], w["m"]
-    updater = None
     if w["surrogate"] == "rbf":
         X, Y = training_set(w, w["centers"], 1)
         updater = SR.Surrogate_update(d, m, kernel_type=w["kernel_type"], solver_type=w.get("solver_type", "direct"),
                                       no_keep=w["centers"])
-        updater.add_arrays(X, Y)
-        sur, _ = updater.update_device()
     else:
         X, Y = training_set(w, 2000, 1)
         updater = SP.Surrogate_update(d, m, max_degree=w["degree"])
-        updater.add_arrays(X, Y)
-        sur, _ = updater.update_device()
+    updater.add_arrays(X, Y)
+    sur, _ = updater.update_device()
     truth = DeviceModel.toy()
-    truth_SOL = None
     if w["truth"] == "rbf":
         Xt, Yt = training_set(w, w["truth_centers"], 2)
         tu = SR.Surrogate_update(d, m, kernel_type=1, solver_type="direct")
         tu.add_arrays(Xt, Yt)
         truth, _ = tu.update_device()
-        truth_SOL = truth.sol_numpy()
-    return updater, sur, truth, truth_SOL
+    return updater, sur, truth
+
+
+class Run:
+    """One measured configuration on this rank: C_ chains of workload w, synchronous or asynchronous collector."""
+
+    def __init__(self, w, C_, rank, world, dev, collector="sync", refit_mode="broadcast", lag=1, precision="f64"):
+        import torch
+
+        from surrdamh_b200.chains import ChainBlock, Proposal, Trace
+        from surrdamh_b200.collector import AsyncCollector, Collector
+        from surrdamh_b200.device import DeviceProblem
+        self.torch = torch
+        self.w, self.C, self.rank, self.world, self.dev = w, C_, rank, world, dev
+        d, m, K = w["d"], w["m"], w["block"]
+        self.d, self.m, self.K = d, m, K
+        self.updater, self.sur, self.truth = build_models(w)
+        self.prob = DeviceProblem(d, **w["problem"], device=dev)
+        self.blk = ChainBlock(self.prob, C_, chain0=rank * C_, seed=2024, device=dev)
+        self.prop = Proposal(d, w["proposal_std"], device=dev)
+        self.col = self.acol = None
+        self.lag = lag if collector == "async" else 0
+        if w["updated"]:
+            self.col = Collector(self.updater, "rbf", d, m, kernel_type=w["kernel_type"], rank=rank, world=world,
+                                 snapshots_per_refit=w["snapshots_per_refit"], refit_mode=refit_mode, device=dev)
+            self.col.model = self.sur
+            if collector == "async":
+                self.acol = AsyncCollector(self.col, dev, lag=lag)
+            self.traces = [Trace(K, C_, d, m, dev, snapshots=True, full=False) for _ in range(self.lag + 1)]
+        else:
+            self.traces = [None]
+        self.flags_only = Trace(K, C_, d, m, dev, snapshots=False, full=False) if not w["updated"] else None
+        self.flush = torch.empty((256 << 20) // 8, dtype=torch.float64, device=dev)      # > 126 MB of L2
+        self.state = {"sur": self.sur, "swapped": False, "b": 0, "drained": 0}
+        self.kern_ev, self.round_ev = [], []
+
+    def one_block(self, timed, host_io=None):
+        """One bench step.  host_io: the e2e variant (pinned buffers).  With the asynchronous collector the snapshots of
+        block b are refitted on the side stream while blocks b+1 .. b+lag run, and the surrogate of round b is
+        switched in at the start of block b + lag + 1."""
+        torch, st, blk, K = self.torch, self.state, self.blk, self.K
+        b = st["b"]
+        st["b"] += 1
+        main = torch.cuda.current_stream()
+        acol, col = self.acol, self.col
+        if acol is not None and b > self.lag:
+            R, new = acol.result(b - self.lag - 1)
+            main.wait_event(R)
+            acol.forget(b - self.lag - 1)
+            if new is not None:
+                st["sur"], st["swapped"] = new, True
+        trace = self.traces[b % len(self.traces)]
+        if trace is None and host_io is not None:
+            trace = self.flags_only
+        self.flush.fill_(1.0)
+        if host_io is not None:
+            blk.u.copy_(host_io["u_in"], non_blocking=True)                  # H2D: chain samples from pinned host memory
+            blk.prepare("DAMH", st["sur"], self.truth)                        # G(u), posteriors of the uploaded samples
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        blk.run("DAMH", K, self.prop, st["sur"], self.truth, trace=trace, refresh_pre=st["swapped"], coresident=acol is not None)
+        e1.record()
+        if timed:
+            self.kern_ev.append((e0, e1, st["swapped"]))
+        st["swapped"] = False
+        if acol is not None:
+            acol.submit(b, trace, K, e1, blk.step0, timed)
+        elif col is not None:
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            if col.round(trace, K, blk.step0):
+                st["sur"], st["swapped"] = col.model, True
+            r1.record()
+            if timed:
+                self.round_ev.append((r0, r1))
+        if host_io is not None:
+            # D2H: what a user gets back per block
+            host_io["u"].copy_(blk.u, non_blocking=True)
+            host_io["counters"].copy_(blk.counters, non_blocking=True)
+            host_io["moments"].copy_(blk.moments, non_blocking=True)
+            host_io["flags"].copy_(trace.flags, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    def drain(self):
+        """Make the sampling stream wait for every collector round issued so far (their surrogates stay queued)."""
+        if self.acol is None:
+            return
+        main = self.torch.cuda.current_stream()
+        for b in sorted(self.acol.results):
+            if b >= self.state["drained"]:
+                main.wait_event(self.acol.result(b)[0])
+        self.state["drained"] = self.state["b"]
+
+    def barrier(self):
+        self.drain()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def timed_region(self, n_steps, host_io=None):
+        torch = self.torch
+        self.barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(n_steps):
+            self.one_block(True, host_io)
+        self.drain()             # the last collector rounds belong to the timed region
+        t1.record()
+        self.barrier()
+        ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def warmup(self, n):
+        self.blk.prepare("DAMH", self.sur, self.truth)
+        for _ in range(n):
+            self.one_block(False)
+
+    def host_buffers(self):
+        torch, blk = self.torch, self.blk
+        if blk.moments is None:
+            blk.moments = torch.zeros((blk.n_mom, blk.C), dtype=torch.float64, device=self.dev)
+        io = {"u_in": torch.empty((self.d, self.C), dtype=torch.float64).pin_memory(),
+              "u": torch.empty((self.d, self.C), dtype=torch.float64).pin_memory(),
+              "counters": torch.empty((4, self.C), dtype=torch.int32).pin_memory(),
+              "moments": torch.empty((blk.n_mom, self.C), dtype=torch.float64).pin_memory(),
+              "flags": torch.empty((self.K, self.C), dtype=torch.uint8).pin_memory()}
+        io["u_in"].copy_(blk.u.cpu())
+        h2d = io["u_in"].numel() * 8
+        d2h = io["u"].numel() * 8 + io["counters"].numel() * 4 + io["moments"].numel() * 8 + io["flags"].numel()
+        return io, int(h2d), int(d2h)
+
+    def measure(self, steps, warmup, e2e_steps):
+        """-> dict of measured numbers for this configuration (device-resident and end-to-end)."""
+        from surrdamh_b200 import _lib as L
+        self.warmup(max(warmup, 3))
+        L.lib().sdb_launch_count(1)
+        wall0 = time.time()
+        ms_total = self.timed_region(steps)
+        wall1 = time.time()
+        launches = int(L.lib().sdb_launch_count(1))
+        kern = [(a.elapsed_time(b), sw) for a, b, sw in self.kern_ev]
+        rounds = [a.elapsed_time(b) for a, b in (self.acol.round_events if self.acol is not None else self.round_ev)]
+        self.kern_ev.clear(); self.round_ev.clear()
+        if self.acol is not None:
+            self.acol.round_events.clear()
+        io, h2d, d2h = self.host_buffers()
+        self.one_block(False, io)
+        ms_e2e = self.timed_region(e2e_steps, io)
+        self.kern_ev.clear(); self.round_ev.clear()
+        if self.acol is not None:
+            self.acol.round_events.clear()
+        failures = 0
+        if self.col is not None:
+            self.col.poll_status(wait=True)
+            failures = sum(1 for s in self.col.status_log if s[1])
+        total = float(self.C) * self.K * steps * self.world
+        return dict(value=total / (ms_total * 1e-3), ms_per_step=ms_total / steps, steps=steps, launches=launches, kern=kern,
+                    rounds=rounds, wall=(wall0, wall1), refit_failures=failures,
+                    e2e=dict(value=float(self.C) * self.K * e2e_steps * self.world / (ms_e2e * 1e-3), unit="chain steps/s",
+                             h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps, ms_per_step=ms_e2e / e2e_steps,
+                             returns="per block and chain: final sample, counters, running first / second moments of the chain, "
+                                     "accept / reject flag of every step"))
+
+
+def flops_per_point(w, sur):
+    d, m = w["d"], w["m"]
+    if w["surrogate"] == "rbf":
+        return w["centers"] * (3 * d + 3 + 2 * m) + m * (2 * d + 1)
+    P = int(sur.alpha.shape[0])
+    return d * w["degree"] + d * (w["degree"] + 1) ** 2 + P * (d + 2 * m)
+
+
+def fp64_peaks(dev):
+    """Live FP64 FMA throughput of this GPU (roofline denominator; MEASURED_PEAKS.json has no FP64 entry)."""
+    import torch
+
+    from surrdamh_b200 import _lib as L
+    info = L.device_info()
+    pb, iters = info["sm_count"] * 8, 20000
+    pout = torch.empty((pb * 256,), dtype=torch.float64, device=dev)
+    out = []
+    for fn in (L.lib().sdb_fp64_probe, L.lib().sdb_fp64_probe3):
+        pout.zero_()
+        L.check(fn(iters, pb, L.ptr(pout), L.stream_handle()))
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        L.check(fn(iters, pb, L.ptr(pout), L.stream_handle()))
+        p1.record()
+        p1.synchronize()
+        out.append(pb * 256 * 8 * 2.0 * iters / (p0.elapsed_time(p1) * 1e-3) / 1e12)
+    return out
+
+
+def kernel_name(w):
+    if w["surrogate"] == "poly" and w["d"] == 2 and w["m"] == 1 and not os.environ.get("SDB_NO_LEAN"):
+        return "chain_lean_kernel<%d,true>" % w["degree"]
+    return "chain_kernel<%d,%d>" % (w["d"], w["m"])
+
+
+def roofline_of(w, run, rec, peak_tf, peak3_tf, headline):
+    d, m, C_, K = w["d"], w["m"], run.C, run.K
+    per_point = flops_per_point(w, run.sur)
+    avg_ms = float(np.mean([k for k, _ in rec["kern"]]))
+    frac_sw = float(np.mean([1.0 if sw else 0.0 for _, sw in rec["kern"]]))
+    flops_launch = float(C_) * (K + frac_sw) * per_point
+    achieved = flops_launch / (avg_ms * 1e-3) / 1e12
+    out = {"bound": "fp64-pipe", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+           "traffic": 123539712 if headline else None, "kernel": kernel_name(w), "kernel_ms": avg_ms,
+           "kernel_share_of_step": avg_ms * len(rec["kern"]) / (rec["ms_per_step"] * rec["steps"]), "flops_per_launch": flops_launch}
+    if headline:
+        out.update({"traffic_note": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the ncu --set full capture in "
+                                    "profiles/r01_chain_kernel_ncu.md; algorithmic bytes = C*K*25 B trace + state = 1.05e8",
+                    "peak_three_register_fma": peak3_tf,
+                    "peak_source": "sdb_fp64_probe (8 independent DFMA chains/thread), measured live in this run; "
+                                   "MEASURED_PEAKS.json has no FP64 entry"})
+    return out
 
 
 def run_ours(args):
@@ -213,9 +569,6 @@ def run_ours(args):
     import torch.distributed as dist
 
     from surrdamh_b200 import _lib as L
-    from surrdamh_b200.chains import ChainBlock, Proposal, Trace, compact_snapshots
-    from surrdamh_b200.collector import Collector
-    from surrdamh_b200.device import DeviceProblem
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -224,287 +577,158 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if not os.environ.get("SDB_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout, which carries the JSON line
+        # NCCL's log (communicator / ring lines at INFO) goes to stderr: stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-    w = dict(WORKLOADS[args.workload])
+    wname = args.workload
+    w = dict(WORKLOADS[wname])
     if args.chains:
         w["chains"] = args.chains
     if args.centers and w["surrogate"] == "rbf":
         w["centers"] = args.centers
     if args.solver and w["surrogate"] == "rbf":
         w["solver_type"] = args.solver
-    d, m, C_, K = w["d"], w["m"], w["chains"], w["block"]
-    updater, sur, truth, truth_SOL = build_models(w)
-    SOL0 = sur.sol_numpy()
+    collector = args.collector or "sync"
+    refit_mode = args.refit_mode or "broadcast"
 
     # ---- CPU baseline (rank 0, N == 1 only), before the timed GPU region -------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile:
-        cpu = cpu_baseline(args.workload, SOL0, truth_SOL, args.cpu_seconds)
+        SOL, truth_SOL, fit_s = cpu_models(WORKLOADS[wname])
+        cpu = cpu_arm(wname, SOL, truth_SOL, args.cpu_seconds)
+        if WORKLOADS[wname]["surrogate"] == "rbf":
+            cpu["refit_s"] = fit_s
+            cpu["refit_note"] = "one full Surrogate_update.update() of the same CPU implementation at n = %d (solver_type 'direct', all host threads)" % WORKLOADS[wname]["centers"]
 
-    prob = DeviceProblem(d, **w["problem"], device=dev)
-    blk = ChainBlock(prob, C_, chain0=rank * C_, seed=2024, device=dev)
-    prop = Proposal(d, w["proposal_std"], device=dev)
-    col = None
-    if w["updated"]:
-        col = Collector(updater if (rank == 0 or world == 1) else None, "rbf", d, m, kernel_type=w["kernel_type"], rank=rank,
-                        world=world, snapshots_per_refit=w["snapshots_per_refit"], refit_mode="broadcast", device=dev)
-        col.model = sur
-    overlap = bool(w["updated"]) and args.overlap
-    traces = [Trace(K, C_, d, m, dev, snapshots=True, full=False) for _ in range(2 if overlap else 1)] if w["updated"] else [None]
-    acol = None
-    if overlap:
-        from surrdamh_b200.collector import AsyncCollector
-        acol = AsyncCollector(col, dev)
-    flush = torch.empty((256 << 20) // 8, dtype=torch.float64, device=dev)      # > 126 MB of L2
-    model = {"sur": sur, "swapped": False, "b": 0, "drained": 0}
-    kern_ms, refit_ms = [], []
-    ev_pool = []
-
-    def one_block(timed, host_io=None):
-        """One bench step.  host_io = (pinned_in, pinned_out_u, pinned_out_cnt): the e2e variant.
-        With the asynchronous collector the snapshots of block b are refitted on the side stream while block b+1
-        runs, and the surrogate of round b is switched in at the start of block b+2."""
-        b = model["b"]
-        model["b"] += 1
-        main = torch.cuda.current_stream()
-        if acol is not None and b >= 2:
-            R, new = acol.result(b - 2)
-            main.wait_event(R)
-            acol.forget(b - 2)
-            if new is not None:
-                model["sur"], model["swapped"] = new, True
-        trace = traces[b % len(traces)]
-        flush.fill_(1.0)
-        if host_io is not None:
-            blk.u.copy_(host_io[0], non_blocking=True)                      # H2D: chain samples from pinned host memory
-            blk.prepare("DAMH", model["sur"], truth)                         # G(u), posteriors of the uploaded samples
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        blk.run("DAMH", K, prop, model["sur"], truth, trace=trace, refresh_pre=model["swapped"], coresident=acol is not None)
-        e1.record()
-        if timed:
-            ev_pool.append((e0, e1, model["swapped"]))
-        model["swapped"] = False
-        if acol is not None:
-            acol.submit(b, trace, K, w["snapshots_per_refit"], e1, blk.step0, timed)
-        elif col is not None:
-            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            r0.record()
-            par, obs, cnt = compact_snapshots(trace, K, w["snapshots_per_refit"])
-            if col.exchange_and_refit(par, obs, cnt, blk.step0):
-                model["sur"], model["swapped"] = col.model, True
-            r1.record()
-            if timed:
-                refit_ms.append((r0, r1))
-        if host_io is not None:
-            host_io[1].copy_(blk.u, non_blocking=True)                       # D2H: samples + counters
-            host_io[2].copy_(blk.counters, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-
-    def drain():
-        """Make the sampling stream wait for every collector round issued so far (their surrogates stay queued)."""
-        if acol is None:
-            return
-        main = torch.cuda.current_stream()
-        for b in range(max(model["drained"], model["b"] - 2), model["b"]):
-            R, _ = acol.result(b)
-            main.wait_event(R)
-        model["drained"] = model["b"]
-
-    def barrier():
-        drain()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def timed_region(n_steps, host_io=None):
-        barrier()
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        for _ in range(n_steps):
-            one_block(True, host_io)
-        drain()             # the last collector rounds belong to the timed region
-        t1.record()
-        barrier()
-        ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    clk_path = os.path.join(tempfile.gettempdir(), "sdb_clocks_%d.csv" % os.getpid())
-    mon = clocks_monitor_start(clk_path) if (rank == 0 and not args.profile) else None
-    blk.prepare("DAMH", sur, truth)
-    for _ in range(max(args.warmup, 3)):
-        one_block(False)
+    run = Run(w, w["chains"], rank, world, dev, collector, refit_mode, args.lag)
     if args.profile:
-        # one bench step between cudaProfilerStart/Stop (ncu --profile-from-start off); nothing is reported
+        run.warmup(max(args.warmup, 3))
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.start()
         for _ in range(args.profile):
-            one_block(False)
+            run.one_block(False)
+        run.drain()
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.stop()
         print(json.dumps({"profile_blocks": args.profile, "note": "no measurement taken in profile mode"}))
         return
-    # ---- FP64 peak probe (roofline denominator), live ---------------------------------------------------
-    info = L.device_info()
-    pb, iters = info["sm_count"] * 8, 20000
-    pout = torch.empty((pb * 256,), dtype=torch.float64, device=dev)
-    L.check(L.lib().sdb_fp64_probe(iters, pb, L.ptr(pout), L.stream_handle()))
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    L.check(L.lib().sdb_fp64_probe(iters, pb, L.ptr(pout), L.stream_handle()))
-    p1.record()
-    p1.synchronize()
-    fp64_peak_tf = pb * 256 * 8 * 2.0 * iters / (p0.elapsed_time(p1) * 1e-3) / 1e12
-    pout.zero_()
-    L.check(L.lib().sdb_fp64_probe3(iters, pb, L.ptr(pout), L.stream_handle()))
-    pout.zero_()
-    p0.record()
-    L.check(L.lib().sdb_fp64_probe3(iters, pb, L.ptr(pout), L.stream_handle()))
-    p1.record()
-    p1.synchronize()
-    fp64_peak3_tf = pb * 256 * 8 * 2.0 * iters / (p0.elapsed_time(p1) * 1e-3) / 1e12
-
-    # ---- timed: device-resident --------------------------------------------------------------------------
-    L.lib().sdb_launch_count(1)
-    wall0 = time.time()
-    ms_total = timed_region(args.steps)
-    wall1 = time.time()
-    launches = int(L.lib().sdb_launch_count(1))
+    clk_path = os.path.join(tempfile.gettempdir(), "sdb_clocks_%d.csv" % os.getpid())
+    mon = clocks_monitor_start(clk_path) if rank == 0 else None
+    peak_tf, peak3_tf = fp64_peaks(dev)
+    e2e_steps = max(2, min(args.steps, 8))
+    rec = run.measure(args.steps, args.warmup, e2e_steps)
     if mon is not None:
         mon.terminate()
         mon.wait()
-    kern = [(a.elapsed_time(b), sw) for a, b, sw in ev_pool]
-    if acol is not None:
-        refit_ms = list(acol.round_ms)
-        acol.round_ms.clear()
-    rf = [a.elapsed_time(b) for a, b in refit_ms]
-    ev_pool.clear(); refit_ms.clear()
 
-    # ---- timed: end to end through host buffers -------------------------------------------------------------
-    pin_in = torch.empty((d, C_), dtype=torch.float64).pin_memory()
-    pin_in.copy_(blk.u.cpu())
-    pin_u = torch.empty((d, C_), dtype=torch.float64).pin_memory()
-    pin_c = torch.empty((4, C_), dtype=torch.int32).pin_memory()
-    io = (pin_in, pin_u, pin_c)
-    one_block(False, io)
-    e2e_steps = max(2, min(args.steps, 8))
-    ms_e2e = timed_region(e2e_steps, io)
-    ev_pool.clear(); refit_ms.clear()
-    if acol is not None:
-        acol.close()
+    # ---- strong scaling: the same 65536 chains split evenly over the ranks ------------------------------------
+    strong = None
+    if world > 1 and w["updated"] and not args.no_extras and w["chains"] % world == 0:
+        srun = Run(w, w["chains"] // world, rank, world, dev, collector, refit_mode, args.lag)
+        srec = srun.measure(args.steps, args.warmup, e2e_steps)
+        strong = {"scaling": "strong", "chains_total": w["chains"], "chains_per_gpu": w["chains"] // world, "value": srec["value"],
+                  "unit": "chain steps/s", "ms_per_step": srec["ms_per_step"], "e2e": srec["e2e"],
+                  "kernel_ms": float(np.mean([k for k, _ in srec["kern"]])),
+                  "round_ms": float(np.mean(srec["rounds"])) if srec["rounds"] else None, "gpu_launches": srec["launches"]}
+        del srun
+
+    # ---- short records of the other single-GPU workloads ---------------------------------------------------------
+    others = {}
+    if world == 1 and not args.no_extras and wname == "cfg3" and not args.chains and not args.centers:
+        for on in ("cfg2", "cfg5"):
+            ow = dict(WORKLOADS[on])
+            orun = Run(ow, ow["chains"], rank, world, dev)
+            orec = orun.measure(10, 3, 2)
+            others[on] = {"config": static_config(on, ow), "value": orec["value"], "unit": "chain steps/s",
+                          "ms_per_step": orec["ms_per_step"], "steps": 10, "e2e": orec["e2e"],
+                          "roofline": roofline_of(ow, orun, orec, peak_tf, peak3_tf, False), "gpu_launches": orec["launches"]}
+            del orun
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    total_steps = float(C_) * K * args.steps * world
-    value = total_steps / (ms_total * 1e-3)
-    e2e_value = float(C_) * K * e2e_steps * world / (ms_e2e * 1e-3)
-    # ---- roofline of the dominant kernel (fused chain kernel), algorithmic FLOPs per SURVEY.md 8(d) ---------------
-    n_c = w.get("centers", 0)
-    if w["surrogate"] == "rbf":
-        per_point = n_c * (3 * d + 3 + 2 * m) + m * (2 * d + 1)
-    else:
-        P = int(sur.alpha.shape[0])
-        per_point = d * w["degree"] + d * (w["degree"] + 1) ** 2 + P * (d + 2 * m)
-    if w["truth"] == "rbf":
-        # the true model is evaluated only after a stage-1 pass; counted at the observed rate below
-        pass
-    avg_ms = float(np.mean([k for k, _ in kern]))
-    frac_sw = float(np.mean([1.0 if sw else 0.0 for _, sw in kern]))
-    flops_launch = float(C_) * (K + frac_sw) * per_point
-    achieved_tf = flops_launch / (avg_ms * 1e-3) / 1e12
+    d, m, C_, K = w["d"], w["m"], w["chains"], w["block"]
+    rl = roofline_of(w, run, rec, peak_tf, peak3_tf, wname == "cfg3" and not args.chains and not args.centers)
+    avg_ms = rl["kernel_ms"]
+    hbm_bytes = float(C_) * K * (25 if w["updated"] else 0) + 2.0 * C_ * (8 * (d + m + 2) + 16)
     out = {
-        "metric": "surrogate-evaluated DAMH chain steps/s", "value": value, "unit": "chain steps/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "metric": METRIC, "value": rec["value"], "unit": "chain steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: %s" % (args.workload, w["name"]), "chains_per_gpu": C_, "lockstep_steps_per_bench_step": K,
-                   "no_parameters": d, "no_observations": m, "centers": n_c or None,
-                   "l2": "256 MiB flush write before every bench step, inside the timed region",
-                   "refit": ("every %d steps: compact + all-gather + thin + dense solve (%s, N=%d) + broadcast; %.2f ms avg per round; %s"
-                             % (K, w.get("solver_type", "direct"), n_c + d + 1, float(np.mean(rf)),
-                                "asynchronous collector: round b runs on a side stream during block b+1, its surrogate is used from block b+2"
-                                if overlap else "synchronous between blocks")) if rf else "frozen surrogate"},
-        "e2e": {"value": e2e_value, "unit": "chain steps/s", "h2d_bytes_per_step": int(pin_in.numel() * 8),
-                "d2h_bytes_per_step": int(pin_u.numel() * 8 + pin_c.numel() * 4), "steps": e2e_steps,
-                "ms_per_step": ms_e2e / e2e_steps},
-        "gpu_launches": launches,
-        "roofline": {"bound": "fp64-pipe", "achieved": achieved_tf, "peak": fp64_peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / fp64_peak_tf,
-                     "traffic": 123539712 if args.workload == "cfg3" and not args.chains and not args.centers else None,
-                     "traffic_note": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the ncu --set full capture "
-                                     "in profiles/r01_chain_kernel_ncu.md; algorithmic bytes = C*K*25 B trace + state = 1.05e8",
-                     "kernel": "chain_kernel<%d,%d>" % (d, m),
-                     "kernel_ms": avg_ms, "kernel_share_of_step": avg_ms * len(kern) / ms_total,
-                     "flops_per_launch": flops_launch, "peak_three_register_fma": fp64_peak3_tf,
-                     "peak_source": "sdb_fp64_probe (8 independent DFMA chains/thread), measured live in this run; "
-                                    "MEASURED_PEAKS.json has no FP64 entry"},
-        "roofline_hbm": {"bound": "hbm", "frac": (float(C_) * K * (25 if w["updated"] else 0) + 2.0 * C_ * (8 * (d + m + 2) + 16))
-                         / (avg_ms * 1e-3) / 1e9 / 6548.2, "achieved": (float(C_) * K * (25 if w["updated"] else 0) + 2.0 * C_ * (8 * (d + m + 2) + 16))
-                         / (avg_ms * 1e-3) / 1e9, "peak": 6548.2, "unit": "GB/s",
+        "config": static_config(wname, w),
+        "e2e": rec["e2e"], "gpu_launches": rec["launches"], "roofline": rl,
+        "roofline_hbm": {"bound": "hbm", "frac": hbm_bytes / (avg_ms * 1e-3) / 1e9 / 6548.2, "achieved": hbm_bytes / (avg_ms * 1e-3) / 1e9,
+                         "peak": 6548.2, "unit": "GB/s",
                          "note": "the same kernel against the measured HBM copy bandwidth of MEASURED_PEAKS.json: algorithmic bytes "
                                  "(flags + snapshot trace, state read + written once per launch) over the launch time -- far from "
                                  "the HBM roofline, which is why the FP64 pipe is the bound reported above"},
-        "clocks": clocks_summary(clk_path, local, wall0, wall1),
+        "clocks": clocks_summary(clk_path, local, *rec["wall"]),
     }
+    if rec["rounds"]:
+        n_c = w["centers"]
+        round_ms = float(np.mean(rec["rounds"]))
+        flop = n_c ** 3 / 3.0
+        out["collector"] = {"mode": collector, "refit_mode": refit_mode, "lag_blocks": run.lag, "round_ms": round_ms,
+                            "rounds": len(rec["rounds"]), "refit_failures": rec["refit_failures"], "solver": w.get("solver_type"),
+                            "system_size": n_c + d + 1,
+                            "what": "select + all-gather + masked thinning + system build + dense solve + broadcast; "
+                                    + ("enqueued on a side stream, surrogate of round b used from block b+%d" % (run.lag + 1)
+                                       if collector == "async" else "between blocks on the sampling stream")}
+        out["roofline_refit"] = {"bound": "fp64-tensor (DMMA)", "achieved": flop / (round_ms * 1e-3) / 1e12, "peak": peak_tf,
+                                 "unit": "TFLOP/s", "frac": flop / (round_ms * 1e-3) / 1e12 / peak_tf, "flops_per_round": flop,
+                                 "round_ms": round_ms,
+                                 "note": "n^3/3 flop of the Cholesky over the WHOLE collector round (exchange, thinning, build, "
+                                         "solve), same live FP64 peak; at n = 4096 the round is latency-bound (DESIGN.md 4.2)"}
+    if strong is not None:
+        out["strong"] = strong
+    if others:
+        out["other_workloads"] = others
     if cpu is not None:
         out["cpu_baseline"] = cpu
+    sys.stdout.flush()
     print(json.dumps(out))
+    sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
 
 def run_reference(args):
-    """The reference arm: the CPU implementation of the same path (numpy oracle = restatement of the
-    reference's classes; the reference itself is pure Python and cannot travel to the GPU box), all host
-    cores, each bench step a bounded sample."""
+    """The reference arm: the reference's own CPU implementation of the path (Algorithm_DAMH.run of the unmodified modules
+    in oracle/_ref; the numpy oracle when that copy is absent), all host cores, each bench step a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w = WORKLOADS[args.workload]
-    # the surrogate the CPU chains evaluate: same synthetic training set, fitted by the oracle on the host
-    from oracle import surrogate_poly as OP
-    from oracle import surrogate_rbf as ORB
-    d, m = w["d"], w["m"]
-    truth_SOL = None
-    if w["surrogate"] == "rbf":
-        X, Y = training_set(w, w["centers"], 1)
-        up = ORB.RbfUpdate(d, m, kernel_type=w["kernel_type"], solver_type="direct")
-    else:
-        X, Y = training_set(w, 2000, 1)
-        up = OP.PolyUpdate(d, m, max_degree=w["degree"])
-    up.add_arrays(X, Y)
-    SOL, _ = up.update()
-    if w["truth"] == "rbf":
-        Xt, Yt = training_set(w, w["truth_centers"], 2)
-        tu = ORB.RbfUpdate(d, m, kernel_type=1, solver_type="direct")
-        tu.add_arrays(Xt, Yt)
-        truth_SOL, _ = tu.update()
+    wname = args.workload
+    w = WORKLOADS[wname]
+    SOL, truth_SOL, fit_s = cpu_models(w)
     cores = len(os.sched_getaffinity(0))
     per_step = max(1.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
-        cpu_baseline(args.workload, SOL, truth_SOL, min(per_step, 1.0), cores)
-    steps, busy = 0, 0.0
+        cpu_arm(wname, SOL, truth_SOL, min(per_step, 1.0), cores)
+    steps, busy, kind = 0.0, 0.0, "port"
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r = cpu_baseline(args.workload, SOL, truth_SOL, per_step, cores)
+        r = cpu_arm(wname, SOL, truth_SOL, per_step, cores)
+        kind = r["kind"]
         steps += r["value"] * per_step
         busy += per_step
     wall = time.perf_counter() - t0
     value = steps / busy
-    sample = "%d processes x %d samples of %.1f s oracle DAMH steps (frozen surrogate, in-process proxies, no MPI hop)" % (
-        cores, args.steps, per_step)
-    out = {"impl": "reference", "metric": "surrogate-evaluated DAMH chain steps/s", "value": value, "unit": "chain steps/s",
+    what = ("the reference's Algorithm_DAMH.run (unmodified modules from oracle/_ref), CSV output on" if kind == "reference"
+            else "numpy oracle DAMH steps")
+    sample = "%d processes x %d samples of %.1f s of %s, in-process proxies (no MPI hop), surrogate frozen between collector swaps" % (
+        cores, args.steps, per_step, what)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "chain steps/s",
            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "%s: %s" % (args.workload, w["name"]), "note": "CPU arm: one chain per host core"},
-           "cpu_baseline": {"value": value, "unit": "chain steps/s", "cores": cores, "kind": "port", "sample": sample},
+           "dtype": "f64", "data": "synthetic", "config": static_config(wname, w),
+           "arm_note": "CPU arm: one chain per host core; the collector's refit is timed separately (refit_s) because the reference "
+                       "runs it in its own process beside the samplers",
+           "cpu_baseline": {"value": value, "unit": "chain steps/s", "cores": cores, "kind": kind, "sample": sample,
+                            "refit_s": fit_s if w["surrogate"] == "rbf" else None},
            "e2e": {"value": value, "unit": "chain steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
@@ -522,9 +746,11 @@ def main():
     ap.add_argument("--solver", default="", choices=["", "direct", "nullspace"], help="dense solver of the RBF refit")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--overlap", action="store_true",
-                    help="asynchronous collector: refit on a side stream with a lag of one block (measured slower on one GPU: "
-                         "the refit's latency-bound kernels starve beside the FP64-bound chain kernel; DESIGN.md section 4.3)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling record (N > 1) and the cfg2 / cfg5 records (N = 1)")
+    ap.add_argument("--collector", default="", choices=["", "sync", "async"],
+                    help="async: the collector round runs on a side stream beside the next block(s)")
+    ap.add_argument("--refit-mode", default="", choices=["", "broadcast", "rotate", "replicated"])
+    ap.add_argument("--lag", type=int, default=1, help="blocks of lag of the asynchronous collector")
     ap.add_argument("--profile", type=int, default=0, help="run this many bench steps inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
     if args.impl == "reference":

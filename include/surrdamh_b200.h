@@ -194,6 +194,27 @@ SDB_API int sdb_snapshot_compact(const uint8_t *d_flags, const double *d_snap_pa
                          int64_t C, int32_t d, int32_t m, double *d_out_par, double *d_out_obs, int64_t cap,
                          int64_t *d_count, int64_t *d_scratch, void *stream);
 
+/* ---- collector round with fixed shapes (no host synchronisation) --------------------------
+ * The sampler side of classes_communication.py:121-135 and the collector's add_data (process_COLLECTOR.py:87-104,
+ * surrogate_rbf.py:76-90) when every buffer has a static size: each rank contributes at most `quota` snapshots per
+ * round (additive configuration key snapshots_per_refit; the reference forwards every snapshot). */
+/* At most `quota` of the valid snapshots of one launch, evenly spaced over their (step, chain) order, into
+ * d_block [(quota + 1) x (d + m)] row-major: row 0 = {rows kept, valid snapshots in the launch, 0...}, rows 1.. =
+ * [parameters | observations], zero beyond the rows kept.  d_scratch: DEVICE int64 [ceil(K*C/1024) + 2]. */
+SDB_API int sdb_snapshot_select(const uint8_t *d_flags, const double *d_snap_par, const double *d_snap_obs, int32_t K,
+                                int64_t C, int32_t d, int32_t m, double *d_block, int64_t quota, int64_t *d_scratch,
+                                void *stream);
+/* Candidate set of a refit: the n0 rows the updater holds (X0 [n0 x d], Y0 [n0 x m]) followed by the gathered blocks of
+ * `world` ranks (each laid out as above) -> d_X [(n0 + world*quota) x d], d_Y [... x m], d_alive (uint8) = 1 for the held
+ * rows and for each rank's kept rows.  d_total (DEVICE int64, may be NULL) = number of new snapshots. */
+SDB_API int sdb_round_candidates(const double *d_X0, const double *d_Y0, int64_t n0, const double *d_gathered, int32_t world,
+                                 int64_t quota, int32_t d, int32_t m, double *d_X, double *d_Y, uint8_t *d_alive,
+                                 int64_t *d_total, void *stream);
+/* Rows with d_keep != 0, in order, into [n_out x d] / [n_out x m] (the deletion at surrogate_rbf.py:117-119 on fixed-size
+ * buffers).  d_count: DEVICE int32 = rows kept (may exceed or fall short of n_out; the caller checks). */
+SDB_API int sdb_rows_compact(const double *d_X, const double *d_Y, const uint8_t *d_keep, int64_t n, int32_t d, int32_t m,
+                             int64_t n_out, double *d_outX, double *d_outY, int32_t *d_count, void *stream);
+
 /* ---- surrogate update ------------------------------------------------------------------ */
 /* Basis matrix PHI [N x P] row-major of the normalised-Hermite tensor basis (surrogate_poly.py:76-79). */
 SDB_API int sdb_poly_basis(const double *d_points, int64_t N, int32_t d, const sdb_model *model, double *d_PHI, void *stream);
@@ -235,6 +256,12 @@ SDB_API int sdb_minres(const double *d_A, int64_t N, const double *d_b, const do
 SDB_API int64_t sdb_rbf_thin_work(int64_t n);
 SDB_API int sdb_rbf_thin(const double *d_X, int64_t n, int32_t d, int64_t no_keep, uint8_t *d_keep, double *d_work,
                          void *stream);
+/* The same on a fixed-size candidate block: rows with d_alive[i] == 0 (d_alive may be NULL = all alive) are absent from
+ * the start (d_keep = 0) and do not count towards no_keep.  drop_coincident != 0 (additive): once no_keep is reached the
+ * removal goes on while the closest remaining pair has distance exactly 0 -- identical snapshots (every lockstep chain
+ * leaving the same start point) would make the saddle matrix singular, where np.linalg.solve raises. */
+SDB_API int sdb_rbf_thin_masked(const double *d_X, int64_t n, int32_t d, int64_t no_keep, const uint8_t *d_alive,
+                                int32_t drop_coincident, uint8_t *d_keep, double *d_work, void *stream);
 
 /* FP64 tensor-pipe GEMM used by the refit: C (column-major, ldc) = beta C + alpha A B,
  * A(i,k) = A[i*sa_m + k*sa_k], B(k,j) = B[k*sb_k + j*sb_n].  nslab > 1: deterministic split-K through

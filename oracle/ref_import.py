@@ -1,9 +1,9 @@
-"""Import the UNMODIFIED reference modules from /root/reference (build container only).
+"""Import the UNMODIFIED reference modules: from /root/reference in the build container, else from the
+git-ignored copy oracle/_ref/ that `python -m oracle.make_ref` made of them (which travels to the GPU box).
 
-TEST INFRASTRUCTURE.  The reference cannot travel to the GPU box, so nothing on
-the `-m gpu` / smoke / bench path may call this; it exists for
-oracle/make_golden.py and for the "live reference" tests that skip themselves
-when /root/reference is absent.
+TEST / BASELINE INFRASTRUCTURE.  Callers: oracle/make_golden.py, the "live reference" tests (which skip
+themselves when neither tree is present), and bench.py's CPU legs (--impl reference, cpu_baseline), which time
+the reference's own classes on the host cores.  Nothing under surrdamh_b200/ imports this.
 
 Three shims are applied before import; the reference files are
 never edited:
@@ -17,11 +17,27 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("SURRDAMH_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _has_reference(root):
+    return os.path.isfile(os.path.join(root, "surrDAMH", "modules", "classes_SAMPLER.py"))
+
+
+def _find_root():
+    if os.environ.get("SURRDAMH_REFERENCE"):
+        return os.environ["SURRDAMH_REFERENCE"]
+    for root in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if _has_reference(root):
+            return root
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, "surrDAMH", "modules", "classes_SAMPLER.py"))
+    return _has_reference(REF_ROOT)
 
 
 _cache = {}

@@ -89,6 +89,10 @@ _SIGNATURES = {
     "sdb_lu_solve": (C.c_int, [_P, _L, _P, _I, _P, _P, _P]),
     "sdb_rbf_thin_work": (C.c_int64, [_L]),
     "sdb_rbf_thin": (C.c_int, [_P, _L, _I, _L, _P, _P, _P]),
+    "sdb_rbf_thin_masked": (C.c_int, [_P, _L, _I, _L, _P, _I, _P, _P, _P]),
+    "sdb_snapshot_select": (C.c_int, [_P, _P, _P, _I, _L, _I, _I, _P, _L, _P, _P]),
+    "sdb_round_candidates": (C.c_int, [_P, _P, _L, _P, _I, _L, _I, _I, _P, _P, _P, _P, _P]),
+    "sdb_rows_compact": (C.c_int, [_P, _P, _P, _L, _I, _I, _L, _P, _P, _P, _P]),
     "sdb_minres": (C.c_int, [_P, _L, _P, _P, _P, C.c_double, _L, _P, _P, _P]),
     "sdb_dgemm": (C.c_int, [_I, _I, _I, C.c_double, _P, _L, _L, _P, _L, _L, C.c_double, _P, _L, _I, _P, _P]),
     "sdb_launch_count": (C.c_int64, [_I]),

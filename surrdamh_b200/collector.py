@@ -4,12 +4,24 @@ refit, refit the surrogate, hand the new model to every rank.
 Counterpart of surrDAMH/process_COLLECTOR.py:57-113 (whenever snapshots arrived: add_data + a FULL
 update(), then push SOL to the samplers) and of the sampler-side batching / double buffer in
 surrDAMH/modules/classes_communication.py:121-150.  Transport: the reference's pickled MPI
-isend/irecv becomes, with one process per GPU,
-    all_gather(counts) + all_gather(fixed-size snapshot blocks)   over NCCL (gloo in the CPU tests)
-    broadcast(sizes) + broadcast(coefficients [, centers])        from rank 0  (refit_mode 'broadcast')
+isend/irecv becomes, with one process per GPU, per round
+    ONE all_gather of fixed-width snapshot blocks (count in a header row)   NCCL (gloo in the CPU tests)
+    ONE broadcast of the packed state [COEFS | centers | observations | status] from the rank on refit duty
 or no broadcast at all when every rank refits the identical gathered set itself ('replicated').
-The reference's timing is a race between busy-polling ranks; here it is a schedule: the sampler
-calls `exchange_and_refit` at fixed step counts, so a run is reproducible.
+
+Two refit paths:
+  fixed-shape (RBF, `snapshots_per_refit` set, updater holding exactly `no_keep` rows, dense solver): every buffer has
+      a static size, nothing synchronises the host -- the round is a chain of kernel launches and two NCCL calls that
+      can be enqueued on a side stream while the chains keep stepping (AsyncCollector).  The refit duty can rotate
+      over the ranks (`refit_mode: "rotate"`), because the packed state makes every rank a full copy of the updater.
+  general (everything else: the reference's unbounded snapshot stream, growing center sets, poly, MINRES): sizes are
+      read back to the host, the model is broadcast from rank 0.
+
+Which snapshots enter a refit when `snapshots_per_refit` = q is set (additive key; the reference forwards every
+snapshot, which is what happens when it is unset): every rank contributes floor(q / world) (at least 1) of its valid
+snapshots, evenly spaced over their (step, chain) order within the block; the gathered set is ordered (rank, step,
+chain).  The reference's timing is a race between busy-polling ranks; here it is a schedule: the sampler calls
+`round()` at fixed step counts, so a run is reproducible.
 """
 import numpy as np
 import torch
@@ -21,21 +33,27 @@ from .device import DeviceModel
 class Collector:
     def __init__(self, updater, surrogate_type, no_parameters, no_observations, kernel_type=0, group=None, rank=0, world=1,
                  snapshots_per_refit=None, refit_mode="broadcast", device=None):
-        self.updater = updater                  # Surrogate_update of this package (owned by rank 0 / every rank)
+        self.updater = updater                  # Surrogate_update of this package
         self.surrogate_type = surrogate_type    # 'poly' | 'rbf'
         self.d, self.m = no_parameters, no_observations
         self.kernel_type = kernel_type
         self.group, self.rank, self.world = group, rank, world
         self.cap = None if snapshots_per_refit is None else int(snapshots_per_refit)
-        self.refit_mode = refit_mode
+        self.quota = None if self.cap is None else max(1, self.cap // world)
+        self.refit_mode = refit_mode            # 'broadcast' (rank 0 refits) | 'rotate' | 'replicated'
         self.device = torch.device(device or "cuda")
         self.model = None                       # the surrogate the chains currently evaluate
         self.no_refits = 0
         self.no_snapshots = 0
-        self.history = []                       # (global_step, snapshots used by the refit)
-        self.refit_ms = []
+        self.history = []                       # (global_step, snapshots offered to the refit | None when only the device knows)
         self.model_factory = self._device_model   # (kind, coefs, centers | degree) -> model; tests stub it on CPU
         self.refit_hook = None                    # optional (par_all, obs_all, refit_index) -> SOL: replaces the fit (parity runs)
+        # fixed-shape rounds
+        self.fixed = False                      # True once every rank holds the packed state
+        self.ring, self.gen = [], 0             # packed states of the last generations (the chains may still read g-1, g-2)
+        self._status_pending = []               # (event, pinned status copy, round index)
+        self.status_log = []                    # host copies of the rounds' status rows, read one round late
+        self.allow_fixed = True
 
     def _device_model(self, kind, coefs, extra):
         if kind == "rbf":
@@ -43,34 +61,33 @@ class Collector:
         return DeviceModel.poly(coefs, int(extra), self.d, device=self.device)
 
     # ---- snapshot exchange ---------------------------------------------------------------------
-    def _gather(self, par, obs, count):
-        """par [cap_local x d], obs [cap_local x m] (valid rows first), count: device int64[1] or int.
-        -> (par_all [n x d], obs_all [n x m]) identical on every rank, rank-major order."""
-        n_local = int(count.item()) if isinstance(count, torch.Tensor) else int(count)
-        n_local = min(n_local, par.shape[0])
-        if self.cap is not None:
-            n_local = min(n_local, self.cap)
-        if self.world == 1:
-            return par[:n_local], obs[:n_local]
-        import torch.distributed as dist
-        counts = torch.zeros((self.world,), dtype=torch.int64, device=par.device)
-        mine = torch.tensor([n_local], dtype=torch.int64, device=par.device)
-        dist.all_gather_into_tensor(counts, mine, group=self.group)
-        counts_h = counts.cpu().numpy()
-        width = int(counts_h.max())
-        if width == 0:
-            return par[:0], obs[:0]
-        block = torch.zeros((width, self.d + self.m), dtype=torch.float64, device=par.device)
-        block[:n_local, :self.d] = par[:n_local]
-        block[:n_local, self.d:] = obs[:n_local]
-        gathered = torch.empty((self.world * width, self.d + self.m), dtype=torch.float64, device=par.device)
-        dist.all_gather_into_tensor(gathered, block, group=self.group)
-        rows = torch.cat([gathered[r * width:r * width + int(counts_h[r])] for r in range(self.world)], dim=0)
-        if self.cap is not None:
-            rows = rows[:self.cap]               # the first `cap` snapshots in (rank, step, chain) order
-        return rows[:, :self.d].contiguous(), rows[:, self.d:].contiguous()
+    def select(self, trace, K):
+        """This rank's block of the round: [(quota + 1) x (d + m)], header row = (rows kept, valid snapshots)."""
+        C_ = trace.C
+        quota = self.quota if self.quota is not None else K * C_
+        block = torch.empty((quota + 1, self.d + self.m), dtype=torch.float64, device=trace.flags.device)
+        scratch = torch.empty(((K * C_ + 1023) // 1024 + 2,), dtype=torch.int64, device=trace.flags.device)
+        L.check(L.lib().sdb_snapshot_select(L.ptr(trace.flags), L.ptr(trace.snap_par), L.ptr(trace.snap_obs), K, C_, self.d, self.m,
+                                            L.ptr(block), quota, L.ptr(scratch), L.stream_handle()))
+        return block
 
-    # ---- refit + distribution --------------------------------------------------------------------
+    def gather(self, block):
+        """[world x (quota + 1) x (d + m)], identical on every rank: the ONE collective of the exchange."""
+        if self.world == 1:
+            return block.unsqueeze(0)
+        import torch.distributed as dist
+        out = torch.empty((self.world * block.shape[0], block.shape[1]), dtype=block.dtype, device=block.device)
+        dist.all_gather_into_tensor(out, block, group=self.group)
+        return out.view(self.world, block.shape[0], block.shape[1])
+
+    @staticmethod
+    def rows_of(gathered, d):
+        """Host-synchronising: the valid rows of a gathered set in (rank, step, chain) order -> (par, obs)."""
+        counts = gathered[:, 0, 0].to(torch.int64).cpu().numpy()
+        rows = torch.cat([gathered[r, 1:1 + int(counts[r])] for r in range(gathered.shape[0])], dim=0)
+        return rows[:, :d].contiguous(), rows[:, d:].contiguous()
+
+    # ---- general path: sizes on the host, model from rank 0 -------------------------------------------------------
     def _broadcast_model(self, model):
         import torch.distributed as dist
         if self.surrogate_type == "rbf":
@@ -90,113 +107,177 @@ class Collector:
         dist.broadcast(coefs, src=0, group=self.group)
         return model if self.rank == 0 else self.model_factory("poly", coefs, deg)
 
-    def exchange_and_refit(self, par, obs, count, global_step=0, timed=False):
-        """One collector round.  Returns True when a new surrogate is in place."""
-        par_all, obs_all = self._gather(par, obs, count)
+    def exchange_and_refit(self, par, obs, count=None, global_step=0):
+        """General path on explicit arrays: par [n x d], obs [n x m] are THIS rank's snapshots of the round (valid rows
+        first; count: device int64[1] or int, default all rows).  Returns True when a new surrogate is in place."""
+        n_local = par.shape[0] if count is None else (int(count.item()) if isinstance(count, torch.Tensor) else int(count))
+        n_local = min(n_local, par.shape[0])
+        quota = self.quota if self.quota is not None else n_local
+        if self.world > 1 and self.quota is None:
+            import torch.distributed as dist
+            mx = torch.tensor([n_local], dtype=torch.int64, device=par.device)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+            quota = int(mx.item())
+        n_local = min(n_local, quota)
+        block = torch.zeros((max(quota, 1) + 1, self.d + self.m), dtype=torch.float64, device=par.device)
+        block[0, 0] = n_local
+        block[1:1 + n_local, :self.d] = par[:n_local]
+        block[1:1 + n_local, self.d:] = obs[:n_local]
+        return self._refit_general(self.gather(block), global_step)
+
+    def _refit_general(self, gathered, global_step):
+        par_all, obs_all = self.rows_of(gathered, self.d)
         if par_all.shape[0] == 0:
             return False
-        ev0 = ev1 = None
-        if timed and torch.cuda.is_available():
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-        model = None
         if self.refit_hook is not None:
             SOL = self.refit_hook(par_all, obs_all, self.no_refits)
             self.model = self.model_factory(self.surrogate_type, SOL[0], SOL[1])
-            self.no_refits += 1
-            self.history.append((global_step, int(par_all.shape[0])))
-            return True
-        if self.world == 1 or self.refit_mode == "replicated" or self.rank == 0:
-            self.updater.add_arrays(par_all, obs_all)
-            model, n = self.updater.update_device()
-            self.no_snapshots = n
-        if self.world > 1 and self.refit_mode != "replicated":
-            model = self._broadcast_model(model)
-        if ev0 is not None:
-            ev1.record()
-            ev1.synchronize()
-            self.refit_ms.append(ev0.elapsed_time(ev1))
-        self.model = model
+        else:
+            model = None
+            if self.world == 1 or self.refit_mode == "replicated" or self.rank == 0:
+                self.updater.add_arrays(par_all, obs_all)
+                model, n = self.updater.update_device()
+                self.no_snapshots = n
+            if self.world > 1 and self.refit_mode != "replicated":
+                model = self._broadcast_model(model)
+            self.model = model
         self.no_refits += 1
         self.history.append((global_step, int(par_all.shape[0])))
         return True
 
+    # ---- fixed-shape path ------------------------------------------------------------------------------------------
+    def _can_go_fixed(self):
+        """Identical on every rank: decided from the model every rank holds, not from rank 0's updater."""
+        up = self.updater
+        return (self.allow_fixed and self.refit_hook is None and self.surrogate_type == "rbf" and self.cap is not None and up is not None
+                and getattr(up, "no_keep", None) is not None and getattr(up, "solver_type", "") in ("direct", "nullspace")
+                and self.model is not None and self.model.centers is not None
+                and int(self.model.centers.shape[0]) == int(up.no_keep) and hasattr(up, "update_round_device"))
+
+    def _enter_fixed(self):
+        """One-off: pack rank 0's (or every replica's) state, hand it to all ranks."""
+        up = self.updater
+        self.ring = [up.new_pack() for _ in range(4)]
+        pack = self.ring[0]
+        if self.world == 1 or self.rank == 0 or self.refit_mode == "replicated":
+            pack.copy_(up.pack_from_state(self.model))
+        if self.world > 1 and self.refit_mode != "replicated":
+            import torch.distributed as dist
+            dist.broadcast(pack, src=0, group=self.group)
+        self.model = up.adopt_pack(pack)
+        self.gen, self.fixed = 0, True
+
+    def duty_rank(self, round_index):
+        return round_index % self.world if self.refit_mode == "rotate" else 0
+
+    def _refit_fixed(self, gathered, global_step):
+        up = self.updater
+        cur = self.ring[self.gen % len(self.ring)]
+        self.gen += 1
+        out = self.ring[self.gen % len(self.ring)]
+        duty = self.duty_rank(self.no_refits)
+        if self.world == 1 or self.refit_mode == "replicated" or self.rank == duty:
+            up.update_round_device(gathered.reshape(-1), self.world, self.quota, cur, out)
+        if self.world > 1 and self.refit_mode != "replicated":
+            import torch.distributed as dist
+            dist.broadcast(out, src=duty, group=self.group)
+        self.model = up.adopt_pack(out)
+        self.no_snapshots = int(up.no_keep)
+        # the round's status row goes to pinned memory asynchronously and is looked at one round later
+        status = up.pack_views(out)[3]
+        if status.is_cuda:
+            pinned = torch.empty((16,), dtype=torch.float64).pin_memory()
+            pinned.copy_(status, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._status_pending.append((ev, pinned, self.no_refits))
+        else:
+            self._status_pending.append((None, status.clone(), self.no_refits))
+        self.poll_status()
+        self.no_refits += 1
+        self.history.append((global_step, None))
+        return True
+
+    def poll_status(self, wait=False):
+        """Move finished rounds' status rows to `status_log` [(round, failed, solver info, rows kept, new snapshots)]."""
+        keep = []
+        for ev, pinned, idx in self._status_pending:
+            if wait and ev is not None:
+                ev.synchronize()
+            if ev is None or ev.query():
+                s = pinned.numpy()
+                self.status_log.append((idx, int(s[0]), int(s[1]), int(s[2]), int(s[3])))
+                if s[0] != 0 and self.updater is not None:
+                    self.updater.round_failures += 1
+            else:
+                keep.append((ev, pinned, idx))
+        self._status_pending = keep
+        return self.status_log
+
+    # ---- one collector round -----------------------------------------------------------------------------------------
+    def round(self, trace, K, global_step=0):
+        """Snapshots of the launch in `trace` -> all ranks -> refit -> new model on every rank.  Returns True when a
+        new surrogate is in place (always, on the fixed-shape path: whether the round had any snapshot is known to the
+        device only; a round without one reproduces the previous coefficients)."""
+        block = self.select(trace, K)
+        if self.world > 1 and self.quota is None:
+            # unbounded (the reference's semantics): blocks are as wide as the busiest rank's count
+            par, obs = block[1:, :self.d], block[1:, self.d:]
+            return self.exchange_and_refit(par.contiguous(), obs.contiguous(), block[0, 0].to(torch.int64).reshape(1), global_step)
+        gathered = self.gather(block)
+        if not self.fixed and self._can_go_fixed():
+            self._enter_fixed()
+        if self.fixed:
+            return self._refit_fixed(gathered, global_step)
+        return self._refit_general(gathered, global_step)
+
     def set_model_from_sol(self, SOL):
         """Start from a given surrogate (reference-shaped SOL list)."""
         self.model = self.model_factory(self.surrogate_type, SOL[0], SOL[1])
+        self.fixed = False
 
 
 class AsyncCollector:
     """The collector as a concurrent actor, like the reference's separate COLLECTOR process
     (process_COLLECTOR.py runs beside the samplers, which keep stepping with the surrogate they have until a
     new one arrives -- classes_communication.py:137-150).  Here the asynchrony is deterministic: the snapshots
-    of block b are refitted on a side CUDA stream WHILE block b+1 is being stepped, and the new surrogate is
-    switched in at the start of block b+2 (a fixed lag of one block), so a run is reproducible.
+    of block b are refitted on a side CUDA stream WHILE the next `lag` blocks are being stepped, and the new surrogate
+    is switched in at the start of block b + lag + 1, so a run is reproducible.
 
-    A host thread drives the side stream, because one collector round contains host synchronisations (snapshot
-    counts, solver status); the sampling thread never blocks on them -- it only makes its stream wait on the
-    round's completion event when it needs that round's surrogate.
+    On the fixed-shape path a round never synchronises the host, so it is simply enqueued on the side stream from the
+    sampling thread; the sampling stream waits on the round's completion event when it needs that round's surrogate.
+    (A general-path round -- the first rounds of a run, while the center set still grows -- blocks the host like the
+    synchronous collector does.)
     """
 
-    def __init__(self, collector, device, stream=None):
-        import queue
-        import threading
+    def __init__(self, collector, device, stream=None, lag=1):
         self.col = collector
         self.device = torch.device(device)
         self.stream = stream if stream is not None else torch.cuda.Stream(device=self.device)
-        self.jobs = queue.Queue()
+        self.lag = int(lag)
         self.results = {}
-        self.cv = threading.Condition()
-        self.error = None
-        self.round_ms = []                    # (start_event, end_event) pairs of the timed rounds
-        self.thread = threading.Thread(target=self._work, daemon=True)
-        self.thread.start()
+        self.round_events = []                # (start_event, end_event) pairs of the timed rounds
 
-    def _work(self):
-        from .chains import compact_snapshots
-        torch.cuda.set_device(self.device)
-        while True:
-            job = self.jobs.get()
-            if job is None:
-                return
-            b, trace, K, cap, chain_done, step, timed = job
-            try:
-                with torch.cuda.stream(self.stream):
-                    self.stream.wait_event(chain_done)
-                    r0 = torch.cuda.Event(enable_timing=True)
-                    r1 = torch.cuda.Event(enable_timing=True)
-                    r0.record()
-                    par, obs, cnt = compact_snapshots(trace, K, cap)
-                    did = self.col.exchange_and_refit(par, obs, cnt, step)
-                    r1.record()
-                    if timed:
-                        self.round_ms.append((r0, r1))
-                    res = (r1, self.col.model if did else None)
-            except BaseException as e:      # surfaced in the sampling thread by result()
-                self.error = e
-                res = (None, None)
-            with self.cv:
-                self.results[b] = res
-                self.cv.notify_all()
-
-    def submit(self, b, trace, K, cap, chain_done_event, step, timed=False):
-        self.jobs.put((b, trace, K, cap, chain_done_event, step, timed))
+    def submit(self, b, trace, K, chain_done_event, step, timed=False):
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(chain_done_event)
+            r0 = r1 = None
+            if timed:
+                r0 = torch.cuda.Event(enable_timing=True)
+                r0.record()
+            did = self.col.round(trace, K, step)
+            r1 = torch.cuda.Event(enable_timing=timed)
+            r1.record()
+            if timed:
+                self.round_events.append((r0, r1))
+        self.results[b] = (r1, self.col.model if did else None)
 
     def result(self, b):
-        """(completion event, new surrogate or None) of round b; waits (host side) until the round has been issued."""
-        with self.cv:
-            while b not in self.results:
-                self.cv.wait(timeout=0.05)
-                if self.error is not None:
-                    raise self.error
-            if self.error is not None:
-                raise self.error
-            return self.results[b]
+        """(completion event, new surrogate or None) of round b."""
+        return self.results[b]
 
     def forget(self, b):
-        with self.cv:
-            self.results.pop(b, None)
+        self.results.pop(b, None)
 
     def close(self):
-        self.jobs.put(None)
-        self.thread.join(timeout=10)
+        self.results.clear()

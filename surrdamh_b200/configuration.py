@@ -11,9 +11,16 @@ Same keys, same defaults, same attribute names, so a reference config file loads
 ADDITIVE keys of this implementation (ignored by the reference, never renames):
   no_chains            chains per GPU (default: the no_samplers argument)
   refit_every          lockstep steps between two surrogate refits (default 64)
-  snapshots_per_refit  at most this many new snapshots enter one refit, taken in (step, chain, rank)
-                       order (default: all)
-  refit_mode           'broadcast' (rank 0 refits, coefficients are broadcast; default) | 'replicated'
+  snapshots_per_refit  at most this many new snapshots enter one refit: every rank contributes
+                       floor(q / world) of its own, evenly spaced over their (step, chain) order within the
+                       block; the gathered set is ordered (rank, step, chain) (default: all, as the reference)
+  refit_mode           'broadcast' (rank 0 refits, the packed state is broadcast; default) | 'rotate' (the
+                       refit duty moves round-robin over the ranks) | 'replicated' (every rank refits)
+  collector_async      true: the refit of block b runs on a side stream while the next blocks step; its
+                       surrogate is used from block b + refit_lag + 1 on (default false: used from block b + 1)
+  refit_lag            blocks of lag of the asynchronous collector (default 1)
+  drop_coincident      remove exactly coincident snapshots before an RBF solve (default true: lockstep chains
+                       leaving a common start point emit identical snapshots, a singular system in the reference)
   seed                 Philox key of the chain RNG (default 0)
   device_solver        false forces the host plugin path even if the solver offers device_model()
 """
@@ -93,5 +100,8 @@ class Configuration:
         self.refit_every = int(conf.get("refit_every", 64))
         self.snapshots_per_refit = conf.get("snapshots_per_refit", None)
         self.refit_mode = conf.get("refit_mode", "broadcast")
+        self.collector_async = bool(conf.get("collector_async", False))
+        self.refit_lag = int(conf.get("refit_lag", 1))
+        self.drop_coincident = bool(conf.get("drop_coincident", True))
         self.seed = int(conf.get("seed", 0))
         self.device_solver = bool(conf.get("device_solver", True))

@@ -69,11 +69,6 @@ extern "C" int sdb_poly_eval(const double *d_points, int64_t N, int32_t d, int32
 // ---------------------------------------------------------------------------------------------------
 // RBF: two-stage ring of center chunks.
 // ---------------------------------------------------------------------------------------------------
-struct rbf_ring_unused {
-    int chunk;          // centers per chunk (even, so every chunk starts 16-byte aligned)
-    size_t stage_bytes; // bytes of one stage (centers + weights, each 16-aligned)
-};
-
 template <int D, int M>
 __global__ void __launch_bounds__(256) rbf_eval_kernel(const double *__restrict__ pts, int64_t N, int d, int m,
                                                        const sdb_model mo, double *__restrict__ out, int L, int chunk) {

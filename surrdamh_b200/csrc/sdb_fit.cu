@@ -417,15 +417,19 @@ extern "C" int sdb_rbf_fit(const double *d_X, const double *d_Y, int64_t n, int3
 // work: nn_dist [n] doubles | nn_idx [n] int32
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) thin_nearest_kernel(const double *__restrict__ X, int n, int d, double *__restrict__ nn_dist,
-                                                           int *__restrict__ nn_idx) {
-    // one warp per row
+                                                           int *__restrict__ nn_idx, const uint8_t *__restrict__ alive) {
+    // one warp per row; rows that are not alive on entry (alive != NULL) neither get nor are a neighbour
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= n) return;
+    if (alive && !alive[row]) {
+        if (lane == 0) { nn_dist[row] = DBL_MAX; nn_idx[row] = INT_MAX; }
+        return;
+    }
     double best = DBL_MAX;
     int bj = INT_MAX;
     for (int j = lane; j < n; j += 32) {
-        if (j == row) continue;
+        if (j == row || (alive && !alive[j])) continue;
         const double r = ref_distance(X + (size_t)row * d, X + (size_t)j * d, d);
         if (r < best) { best = r; bj = j; }   // j ascending per lane: first minimum kept
     }
@@ -463,12 +467,14 @@ __device__ __forceinline__ void block_argmin(double &best, int &bidx, double *rv
 // shared memory (use_smem), so an iteration costs a handful of barriers instead of L2 round trips.
 __global__ void __launch_bounds__(1024, 1) thin_remove_kernel(const double *__restrict__ Xg, int n, int d, int no_keep,
                                                               double *__restrict__ nn_dist_g, int *__restrict__ nn_idx_g,
-                                                              uint8_t *__restrict__ keep_g, int use_smem) {
+                                                              uint8_t *__restrict__ keep_g, int use_smem,
+                                                              const uint8_t *__restrict__ alive_g, int dedupe) {
     extern __shared__ __align__(16) unsigned char thin_sm[];
     __shared__ double rv[32];
     __shared__ int rr[32];
     __shared__ int todo[1024];
     __shared__ int ntodo;
+    __shared__ int nalive;
     const int tid = threadIdx.x;
     const double *X = Xg;
     double *nn_dist = nn_dist_g;
@@ -483,10 +489,22 @@ __global__ void __launch_bounds__(1024, 1) thin_remove_kernel(const double *__re
         for (int i = tid; i < n; i += blockDim.x) { nn_dist[i] = nn_dist_g[i]; nn_idx[i] = nn_idx_g[i]; }
         X = Xs;
     }
-    for (int i = tid; i < n; i += blockDim.x) keep[i] = 1;
-    if (tid == 0) ntodo = 0;
+    if (tid == 0) { ntodo = 0; nalive = 0; }
     __syncthreads();
-    for (int it = 0; it < n - no_keep; ++it) {
+    {
+        int mine = 0;
+        for (int i = tid; i < n; i += blockDim.x) {
+            const uint8_t a = alive_g ? (alive_g[i] != 0) : 1;
+            keep[i] = a;
+            mine += a;
+        }
+        if (mine) atomicAdd(&nalive, mine);
+    }
+    __syncthreads();
+    // rows dead on entry do not count (the collector's fixed-shape candidate block); dedupe: past the quota the loop goes on
+    // while the closest pair coincides (distance exactly 0), so that no two identical rows reach the saddle matrix
+    const int n_remove = nalive - no_keep;
+    for (int it = 0;; ++it) {
         // global minimum over alive rows; ties -> smallest row (= the first flat arg-min of the reference)
         double best = DBL_MAX;
         int brow = INT_MAX;
@@ -495,6 +513,7 @@ __global__ void __launch_bounds__(1024, 1) thin_remove_kernel(const double *__re
         block_argmin(best, brow, rv, rr);
         const int v = brow;
         if (v == INT_MAX) break;  // fewer than two alive points
+        if (it >= n_remove && !(dedupe && best == 0.0)) break;
         if (tid == 0) keep[v] = 0;
         // rows whose nearest neighbour was the victim must be rescanned (usually one or two rows); collected in one
         // pass, repeated only if more than 1024 rows pointed at the victim
@@ -581,11 +600,13 @@ static_assert(THF_T == 512, "the owner of point i is thread i & 511, slot i >> 9
 template <int D, int KT>
 __global__ void __maxnreg__(KT <= 9 ? 72 : 128) thin_remove_fast_kernel(const double *__restrict__ Xg, int n, int dd, int no_keep,
                                                                     const double *__restrict__ nn_dist_g,
-                                                                    const int *__restrict__ nn_idx_g, uint8_t *__restrict__ keep_g) {
+                                                                    const int *__restrict__ nn_idx_g, uint8_t *__restrict__ keep_g,
+                                                                    const uint8_t *__restrict__ alive_g, int dedupe) {
     extern __shared__ __align__(16) unsigned char thin_sm[];
     __shared__ thf_red R;
     __shared__ int todo[1024];
     __shared__ int ntodo;
+    __shared__ int nalive;
     const int d = D ? D : dd;
     const int tid = threadIdx.x;
     double *Xs = (double *)thin_sm;                    // the only per-point array in shared memory: the coordinates
@@ -594,18 +615,27 @@ __global__ void __maxnreg__(KT <= 9 ? 72 : 128) thin_remove_fast_kernel(const do
     const int kmax = (n + THF_T - 1) / THF_T;
     double nd[KT];
     int ni[KT];
-#pragma unroll
-    for (int k = 0; k < KT; ++k) {
-        const int i = tid + k * THF_T;
-        ni[k] = i < n ? nn_idx_g[i] : INT_MAX;
-        nd[k] = (i < n && ni[k] != INT_MAX) ? nn_dist_g[i] : INF;
-        if (i < n) keep_g[i] = 1;
-    }
+    if (tid == 0) { ntodo = 0; nalive = 0; }
     for (int e = tid; e < n * d; e += THF_T) Xs[e] = Xg[e];
-    if (tid == 0) ntodo = 0;
     __syncthreads();
+    {
+        int mine = 0;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            const int i = tid + k * THF_T;
+            const bool a = i < n && (!alive_g || alive_g[i]);
+            ni[k] = a ? nn_idx_g[i] : INT_MAX;           // rows dead on entry carry INT_MAX / DBL_MAX (thin_nearest_kernel)
+            nd[k] = (a && ni[k] != INT_MAX) ? nn_dist_g[i] : INF;
+            if (i < n) keep_g[i] = a;
+            if (i < n && !a) Xs[(size_t)i * d] = THF_POISON;   // like a removed point: no scan has to test a flag
+            mine += a;
+        }
+        if (mine) atomicAdd(&nalive, mine);
+    }
+    __syncthreads();
+    const int n_remove = nalive - no_keep;
     int buf = 0;
-    for (int it = 0; it < n - no_keep; ++it) {
+    for (int it = 0;; ++it) {
         // global minimum of the nearest-neighbour distances; ties -> smallest row (the first flat arg-min of the reference)
         double best = INF;
         int brow = INT_MAX;
@@ -620,6 +650,7 @@ __global__ void __maxnreg__(KT <= 9 ? 72 : 128) thin_remove_fast_kernel(const do
         buf ^= 1;
         const int v = brow;
         if (v == INT_MAX) break;                // fewer than two alive points (uniform)
+        if (it >= n_remove && !(dedupe && best == 0.0)) break;      // uniform: thf_argmin broadcasts (best, brow)
         {
             const bool owner = tid == (v & (THF_T - 1));
             if (owner) { keep_g[v] = 0; Xs[(size_t)v * d] = THF_POISON; }
@@ -700,26 +731,27 @@ __global__ void __maxnreg__(KT <= 9 ? 72 : 128) thin_remove_fast_kernel(const do
 
 extern "C" int64_t sdb_rbf_thin_work(int64_t n) { return n + n / 2 + 64; }
 
-extern "C" int sdb_rbf_thin(const double *d_X, int64_t n, int32_t d, int64_t no_keep, uint8_t *d_keep, double *d_work,
-                            void *stream) {
+static int thin_impl(const double *d_X, int64_t n, int32_t d, int64_t no_keep, const uint8_t *d_alive, int dedupe,
+                     uint8_t *d_keep, double *d_work, void *stream) {
     SDB_CHECK_ARG(d_X && d_keep && d_work, "sdb_rbf_thin: NULL pointer");
     SDB_CHECK_ARG(n >= 1 && n < (1 << 30) && no_keep >= 0, "sdb_rbf_thin: bad sizes");
     SDB_CHECK_LIMIT(d >= 1 && d <= SDB_MAX_D, "sdb_rbf_thin: d=%d outside limits", d);
     cudaStream_t st = (cudaStream_t)stream;
     double *nn_dist = d_work;
     int *nn_idx = (int *)(d_work + n);
-    if (no_keep >= n) {
-        SDB_CUDA(cudaMemsetAsync(d_keep, 1, (size_t)n, st));
+    if (no_keep >= n && !dedupe) {
+        if (d_alive) SDB_CUDA(cudaMemcpyAsync(d_keep, d_alive, (size_t)n, cudaMemcpyDeviceToDevice, st));
+        else SDB_CUDA(cudaMemsetAsync(d_keep, 1, (size_t)n, st));
         return SDB_OK;
     }
     sdb_count_launch();
-    thin_nearest_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(d_X, (int)n, d, nn_dist, nn_idx);
+    thin_nearest_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(d_X, (int)n, d, nn_dist, nn_idx, d_alive);
     sdb_device_props dp;
     int rc = sdb_get_device_props(&dp);
     if (rc) return rc;
     const size_t need_fast = (size_t)n * (size_t)d * 8 + 16;
     if (n <= THF_T * THF_K && need_fast + 12288 <= (size_t)dp.smem_optin) {
-        void (*fn)(const double *, int, int, int, const double *, const int *, uint8_t *);
+        void (*fn)(const double *, int, int, int, const double *, const int *, uint8_t *, const uint8_t *, int);
         if (n <= THF_T * 9)
             fn = d == 1 ? thin_remove_fast_kernel<1, 9> : d == 2 ? thin_remove_fast_kernel<2, 9> : d == 3 ? thin_remove_fast_kernel<3, 9>
                  : d == 4 ? thin_remove_fast_kernel<4, 9> : thin_remove_fast_kernel<0, 9>;
@@ -728,7 +760,7 @@ extern "C" int sdb_rbf_thin(const double *d_X, int64_t n, int32_t d, int64_t no_
                  : d == 3 ? thin_remove_fast_kernel<3, THF_K> : d == 4 ? thin_remove_fast_kernel<4, THF_K> : thin_remove_fast_kernel<0, THF_K>;
         SDB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_fast));
         sdb_count_launch();
-        fn<<<1, THF_T, need_fast, st>>>(d_X, (int)n, d, (int)no_keep, nn_dist, nn_idx, d_keep);
+        fn<<<1, THF_T, need_fast, st>>>(d_X, (int)n, d, (int)no_keep, nn_dist, nn_idx, d_keep, d_alive, dedupe);
         SDB_CUDA(cudaGetLastError());
         return SDB_OK;
     }
@@ -737,7 +769,18 @@ extern "C" int sdb_rbf_thin(const double *d_X, int64_t n, int32_t d, int64_t no_
     SDB_CUDA(cudaFuncSetAttribute((const void *)thin_remove_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(use_smem ? need : 0)));
     sdb_count_launch();
-    thin_remove_kernel<<<1, 1024, use_smem ? need : 0, st>>>(d_X, (int)n, d, (int)no_keep, nn_dist, nn_idx, d_keep, use_smem);
+    thin_remove_kernel<<<1, 1024, use_smem ? need : 0, st>>>(d_X, (int)n, d, (int)no_keep, nn_dist, nn_idx, d_keep, use_smem,
+                                                             d_alive, dedupe);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
+}
+
+extern "C" int sdb_rbf_thin(const double *d_X, int64_t n, int32_t d, int64_t no_keep, uint8_t *d_keep, double *d_work,
+                            void *stream) {
+    return thin_impl(d_X, n, d, no_keep, nullptr, 0, d_keep, d_work, stream);
+}
+
+extern "C" int sdb_rbf_thin_masked(const double *d_X, int64_t n, int32_t d, int64_t no_keep, const uint8_t *d_alive,
+                                   int32_t drop_coincident, uint8_t *d_keep, double *d_work, void *stream) {
+    return thin_impl(d_X, n, d, no_keep, d_alive, drop_coincident != 0, d_keep, d_work, stream);
 }

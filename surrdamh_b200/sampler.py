@@ -3,7 +3,7 @@
 Host-side counterpart of surrDAMH/process_SAMPLER.py:25-88 (build problem / proposal / proxies, initial
 samples, run the stages of `samplers_list` in order handing `current_sample` on) with the chain loop
 of classes_SAMPLER.py:147-220 executed by the fused CUDA kernel (csrc/sdb_chain.cu) for all chains
-at once, and the collector round-trip (process_COLLECTOR.py) reduced to Collector.exchange_and_refit.
+at once, and the collector round-trip (process_COLLECTOR.py) reduced to Collector.round.
 
 Two data paths per stage:
   fused : the solver plugin offers device_model() -> K steps per kernel launch, G evaluated in-kernel
@@ -11,8 +11,8 @@ Two data paths per stage:
           per step: PROPOSE kernel, host G for the proposals that passed the surrogate test, DECIDE kernel
 Schedule (deterministic; SURVEY.md section 7 trap 7): in a stage with surrogate_is_updated the snapshots of every
 `refit_every` steps (and of the last, shorter block) are exchanged and the surrogate is refitted;
-the new model is used from the next step on.  A DAMH stage with no fitted surrogate is an error, as
-in the reference (trap 10) -- unless snapshots are already queued, in which case one refit is forced.
+the new model is used from the next step on (`collector_async`: from `refit_lag` blocks later, the
+refit running beside the chains).  A DAMH stage with no fitted surrogate is an error, as in the reference (trap 10).
 """
 import time
 
@@ -20,8 +20,8 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .chains import ChainBlock, Proposal, Trace, compact_snapshots
-from .collector import Collector
+from .chains import ChainBlock, Proposal, Trace
+from .collector import AsyncCollector, Collector
 from .device import DeviceProblem
 from .lhs_normal import lhs_normal
 
@@ -75,10 +75,12 @@ class LockstepSampler:
         if conf.use_surrogate:
             kt = conf.surr_updater_parameters.get("kernel_type", 0) if conf.surrogate_type == "rbf" else 0
             self.apply_kernel_type = conf.surr_solver_parameters.get("kernel_type", 0) if conf.surrogate_type == "rbf" else 0
-            updater = None
-            if world == 1 or rank == 0 or conf.refit_mode == "replicated":
-                kw = {k: v for k, v in conf.surr_updater_parameters.items() if k not in ("no_parameters", "no_observations")}
-                updater = conf.surr_updater_init(self.d, self.m, **kw)
+            # every rank owns an updater: rank 0 (or every replica) refits on the general path, any rank can on the
+            # fixed-shape path, where the packed state travels with the broadcast
+            kw = {k: v for k, v in conf.surr_updater_parameters.items() if k not in ("no_parameters", "no_observations")}
+            if conf.surrogate_type == "rbf":
+                kw.setdefault("drop_coincident", conf.drop_coincident)
+            updater = conf.surr_updater_init(self.d, self.m, **kw)
             self.collector = Collector(updater, conf.surrogate_type, self.d, self.m, kernel_type=self.apply_kernel_type,
                                        group=group, rank=rank, world=world, snapshots_per_refit=conf.snapshots_per_refit,
                                        refit_mode=conf.refit_mode, device=self.device)
@@ -114,7 +116,7 @@ class LockstepSampler:
         self.no_G_calls_host += params.shape[0]
         return out
 
-    def run_stage(self, i, st, timed_refit=False):
+    def run_stage(self, i, st):
         kind, n_steps = st["type"], int(st["max_samples"])
         time_limit = float(st.get("time_limit", float("inf")))
         blk, col = self.block, self.collector
@@ -138,15 +140,31 @@ class LockstepSampler:
         R = self.conf.refit_every if collects else min(n_steps, 1024)
         refits0 = col.no_refits if col is not None else 0
         done, swapped = 0, False
-        trace = None
+        use_async = collects and self.conf.collector_async and self.truth is not None
+        acol = AsyncCollector(col, self.device, lag=self.conf.refit_lag) if use_async else None
+        traces, b = [], 0
+        main = torch.cuda.current_stream(self.device)
         while done < n_steps:
             K = min(R, n_steps - done)
             need_trace = collects or self.trace_sink is not None
-            if need_trace and (trace is None or trace.K < K):
-                trace = Trace(K, self.C, self.d, self.m, self.device, snapshots=collects, full=self.trace_sink is not None or self.truth is None)
+            trace = None
+            if need_trace:
+                slot = b % (acol.lag + 1) if acol is not None else 0        # a round still reads the trace of its block
+                while len(traces) <= slot:
+                    traces.append(None)
+                if traces[slot] is None or traces[slot].K < K:
+                    traces[slot] = Trace(K, self.C, self.d, self.m, self.device, snapshots=collects,
+                                         full=self.trace_sink is not None or self.truth is None)
+                trace = traces[slot]
+            if acol is not None and b > acol.lag:
+                ev, new = acol.result(b - acol.lag - 1)
+                main.wait_event(ev)
+                acol.forget(b - acol.lag - 1)
+                if new is not None and kind == "DAMH":
+                    surrogate, swapped = new, True
             strm = None if self.streams is None else self.streams(i, done, K)
             if self.truth is not None:
-                blk.run(kind, K, prop, surrogate, self.truth, trace=trace if need_trace else None, streams=strm, refresh_pre=swapped)
+                blk.run(kind, K, prop, surrogate, self.truth, trace=trace, streams=strm, refresh_pre=swapped)
             else:
                 self._run_split(kind, K, prop, surrogate, trace, strm, swapped, collects)
             swapped = False
@@ -154,29 +172,54 @@ class LockstepSampler:
                 self.trace_sink(i, done, K, trace)
             done += K
             self.global_step += K
-            if collects:
-                par, obs, cnt = compact_snapshots(trace, K, self._snapshot_capacity(K))
-                if col.exchange_and_refit(par, obs, cnt, self.global_step, timed=timed_refit):
+            if acol is not None:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                acol.submit(b, trace, K, ev, self.global_step)
+            elif collects:
+                if col.round(trace, K, self.global_step):
                     if kind == "DAMH":
                         surrogate, swapped = col.model, True
-            if time_limit != float("inf"):
-                # the limit is wall time of finished work (classes_SAMPLER.py:156,215 checks it every step): wait for this
-                # block, otherwise the host would queue blocks far past the limit
-                torch.cuda.current_stream(self.device).synchronize()
-                if time.time() - t0 > time_limit:
-                    break
+            b += 1
+            if time_limit != float("inf") and self._time_is_up(t0, time_limit):
+                break
+        if acol is not None:
+            # the stage ends with every issued round finished and its surrogate in place (the next stage starts from it)
+            for bb in sorted(acol.results):
+                main.wait_event(acol.result(bb)[0])
+            acol.close()
         torch.cuda.synchronize(self.device)
+        if col is not None:
+            col.poll_status(wait=True)
         if hasattr(self.trace_sink, "end_stage"):
             self.trace_sink.end_stage(i, st, self, done)
         res = StageResult(i, kind, done, blk.counters_numpy(), time.time() - t0, (col.no_refits - refits0) if col is not None else 0)
         self.results.append(res)
         return res
 
-    def _snapshot_capacity(self, K):
-        cap = K * self.C
-        if self.collector.cap is not None:
-            cap = min(cap, self.collector.cap)
-        return cap
+    def _time_is_up(self, t0, time_limit):
+        """classes_SAMPLER.py:156,215 checks wall time of finished work after every step; here after every block, and
+        the decision is COLLECTIVE (max over ranks), because the collector round inside the loop is: a rank leaving
+        alone would pair its next collectives with the wrong block.  The stream is only synchronised when the host is
+        within one block's duration of the limit (or has no estimate yet); queued-but-unfinished blocks are few since
+        every round's gather keeps the ranks in step."""
+        elapsed = time.time() - t0
+        est = getattr(self, "_block_seconds", None)
+        if est is None or elapsed + 4.0 * est > time_limit:
+            torch.cuda.current_stream(self.device).synchronize()
+            now = time.time() - t0
+            nb = getattr(self, "_blocks_seen", 0) + 1
+            self._blocks_seen = nb
+            self._block_seconds = now / nb if est is None else max(est, 0.0) * 0.5 + 0.5 * (now - getattr(self, "_last_sync", 0.0))
+            self._last_sync = now
+            elapsed = now
+        up = elapsed > time_limit
+        if self.world > 1:
+            import torch.distributed as dist
+            flag = torch.tensor([1 if up else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            up = bool(flag.item())
+        return up
 
     def _run_split(self, kind, K, prop, surrogate, trace, strm, swapped, collects):
         """K steps with the true model evaluated by the host plugin (one step per kernel pair)."""
@@ -201,8 +244,8 @@ class LockstepSampler:
                 if collects:
                     trace.snap_par[k], trace.snap_obs[k] = one.snap_par[0], one.snap_obs[0]
 
-    def run(self, timed_refit=False):
+    def run(self):
         """All stages of samplers_list (process_SAMPLER.py:53-88)."""
         for i, st in enumerate(self.conf.list_alg):
-            self.run_stage(i, st, timed_refit=timed_refit)
+            self.run_stage(i, st)
         return self.results

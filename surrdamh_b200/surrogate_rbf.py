@@ -55,7 +55,7 @@ class Surrogate_apply:
 
 class Surrogate_update:
     def __init__(self, no_parameters, no_observations, initial_iteration=None, no_keep=None, expensive=False,
-                 kernel_type=0, solver_tol_exp=-6, solver_type="minres", max_iterations=None):
+                 kernel_type=0, solver_tol_exp=-6, solver_type="minres", max_iterations=None, drop_coincident=False):
         L.require_cuda()
         self.no_parameters = no_parameters
         self.no_observations = no_observations
@@ -66,6 +66,11 @@ class Surrogate_update:
         self.solver_tol_exp = solver_tol_exp
         self.solver_type = solver_type
         self.max_iterations = max_iterations
+        # additive: remove exactly coincident snapshots before the solve (the lockstep sampler switches it on: all chains
+        # leaving one start point emit the same displaced snapshot, which makes the saddle matrix singular)
+        self.drop_coincident = bool(drop_coincident)
+        self.fallbacks = 0                  # null-space Cholesky rounds that fell back to the pivoted LU
+        self.round_failures = 0             # fixed-shape rounds whose solve failed (previous surrogate kept)
         self.no_processed = 0
         self._par = torch.empty((0, no_parameters), dtype=torch.float64, device="cuda")
         self._obs = torch.empty((0, no_observations), dtype=torch.float64, device="cuda")
@@ -97,24 +102,47 @@ class Surrogate_update:
         self._new_obs.append(o)
 
     # ---- pieces (each one kernel family) ---------------------------------------------------------
-    def _thin(self, stream):
+    def _thin(self):
         n, d = self._par.shape
         keep = torch.empty((n,), dtype=torch.uint8, device="cuda")
         work = torch.empty((L.lib().sdb_rbf_thin_work(n),), dtype=torch.float64, device="cuda")
-        L.check(L.lib().sdb_rbf_thin(L.ptr(self._par), n, d, int(self.no_keep), L.ptr(keep), L.ptr(work),
-                                     L.stream_handle(stream)))
+        no_keep = n if self.no_keep is None else int(self.no_keep)
+        L.check(L.lib().sdb_rbf_thin_masked(L.ptr(self._par), n, d, no_keep, None, int(self.drop_coincident), L.ptr(keep),
+                                            L.ptr(work), L.stream_handle()))
         mask = keep.bool()
         self._par = self._par[mask].contiguous()
         self._obs = self._obs[mask].contiguous()
 
+    def _scratch(self, need):
+        if self._work is None or self._work.numel() < need:
+            self._work = torch.empty((need,), dtype=torch.float64, device="cuda")
+        return self._work
+
+    def _solve_dense(self, Xb, Yb, Cb, n, info):
+        """Dense solve of the saddle system for the n rows of (Xb, Yb) into Cb; launches only (info stays on the device)."""
+        d, m = self.no_parameters, self.no_observations
+        if self.solver_type == "nullspace" and int(self.kernel_type) in (0, 1, 4, 5, 6) and n > d + 1:
+            work = self._scratch(L.lib().sdb_rbf_fit_nullspace_work(n, d, m))
+            L.check(L.lib().sdb_rbf_fit_nullspace(L.ptr(Xb), L.ptr(Yb), n, d, m, int(self.kernel_type), L.ptr(Cb), L.ptr(work),
+                                                  L.ptr(info), L.stream_handle()))
+            return "nullspace"
+        work = self._scratch(L.lib().sdb_rbf_fit_work(n, d, m))
+        L.check(L.lib().sdb_rbf_fit(L.ptr(Xb), L.ptr(Yb), n, d, m, int(self.kernel_type), L.ptr(Cb), L.ptr(work), L.ptr(info),
+                                    L.stream_handle()))
+        return "lu"
+
     def update_device(self, stream=None):
-        """-> (DeviceModel, no_snapshots); nothing leaves HBM."""
+        """-> (DeviceModel, no_snapshots); nothing leaves HBM.  A singular system raises np.linalg.LinAlgError, as
+        np.linalg.solve does at surrogate_rbf.py:130 (the updater's state then holds the offending rows, as there)."""
+        if stream is not None and stream != torch.cuda.current_stream():
+            with torch.cuda.stream(stream):          # every torch op and every kernel below goes to ONE stream
+                return self.update_device()
         d, m = self.no_parameters, self.no_observations
         self._par = torch.cat([self._par] + self._new_par, dim=0).contiguous()
         self._obs = torch.cat([self._obs] + self._new_obs, dim=0).contiguous()
         self._new_par, self._new_obs = [], []
-        if self.no_keep is not None and self._par.shape[0] > self.no_keep:
-            self._thin(stream)
+        if (self.no_keep is not None and self._par.shape[0] > self.no_keep) or (self.drop_coincident and self._par.shape[0] > 1):
+            self._thin()
         n = self.no_processed = self._par.shape[0]
         N = n + d + 1
         info = self._info_buf
@@ -127,32 +155,25 @@ class Surrogate_update:
         _, Xb, Yb, Cb = self._io
         Xb.copy_(self._par)
         Yb.copy_(self._obs)
-
-        def scratch(need):
-            if self._work is None or self._work.numel() < need:
-                self._work = torch.empty((need,), dtype=torch.float64, device="cuda")
-            return self._work
-
-        done = False
-        if self.solver_type == "nullspace" and int(self.kernel_type) in (0, 1, 4, 5, 6) and n > d + 1:
-            # additive solver: null-space method + Cholesky (no pivoting); falls back to the pivoted LU below
-            # if the projected kernel matrix is numerically not definite
-            work = scratch(L.lib().sdb_rbf_fit_nullspace_work(n, d, m))
-            L.check(L.lib().sdb_rbf_fit_nullspace(L.ptr(Xb), L.ptr(Yb), n, d, m, int(self.kernel_type), L.ptr(Cb), L.ptr(work),
-                                                  L.ptr(info), L.stream_handle(stream)))
-            done = int(info[0].item()) == 0
-            self.fallbacks = getattr(self, "fallbacks", 0) + (0 if done else 1)
-        if done:
-            pass
-        elif self.solver_type in ("direct", "nullspace"):
-            work = scratch(L.lib().sdb_rbf_fit_work(n, d, m))
-            L.check(L.lib().sdb_rbf_fit(L.ptr(Xb), L.ptr(Yb), n, d, m, int(self.kernel_type), L.ptr(Cb), L.ptr(work), L.ptr(info),
-                                        L.stream_handle(stream)))
+        if self.solver_type in ("direct", "nullspace"):
+            how = self._solve_dense(Xb, Yb, Cb, n, info)
+            failed = int(info[0].item()) != 0
+            if failed and how == "nullspace":
+                # the projected kernel matrix is numerically not definite: the pivoted LU of the reference's 'direct' solver
+                self.fallbacks += 1
+                info.zero_()
+                work = self._scratch(L.lib().sdb_rbf_fit_work(n, d, m))
+                L.check(L.lib().sdb_rbf_fit(L.ptr(Xb), L.ptr(Yb), n, d, m, int(self.kernel_type), L.ptr(Cb), L.ptr(work),
+                                            L.ptr(info), L.stream_handle()))
+                failed = int(info[0].item()) != 0
+            if failed or not bool(torch.isfinite(Cb).all().item()):
+                self.last_info = info.cpu().numpy()
+                raise np.linalg.LinAlgError("Singular matrix")          # what np.linalg.solve raises
         else:
             S = torch.empty((N, N), dtype=torch.float64, device="cuda")
             rhs = torch.empty((m, N), dtype=torch.float64, device="cuda")       # one contiguous column per observation
             L.check(L.lib().sdb_rbf_system(L.ptr(Xb), L.ptr(Yb), n, d, m, int(self.kernel_type), L.ptr(S), L.ptr(rhs),
-                                           L.stream_handle(stream)))
+                                           L.stream_handle()))
             x = torch.zeros((m, N), dtype=torch.float64, device="cuda")
             x0 = None
             if self.initial_iteration is not None:
@@ -161,16 +182,99 @@ class Surrogate_update:
             maxiter = int(self.max_iterations) if self.max_iterations is not None else 5 * N   # scipy's default
             for k in range(m):
                 L.check(L.lib().sdb_minres(L.ptr(S), N, L.ptr(rhs[k]), L.ptr(x0), L.ptr(x[k]), float(10.0 ** self.solver_tol_exp),
-                                           maxiter, L.ptr(work), L.ptr(info), L.stream_handle(stream)))
+                                           maxiter, L.ptr(work), L.ptr(info), L.stream_handle()))
             Cb.copy_(x.t())
         COEFS = Cb.clone()
         self._info = info
         mo = DeviceModel(L.MODEL_RBF, kernel_type=self.kernel_type, coefs=COEFS, centers=self._par.clone(), d=d, m=m)
         return mo, n
 
+    # ---- fixed-shape round: no host synchronisation ----------------------------------------------------------------
+    # Once the updater holds exactly no_keep rows, a refit has static shapes: candidates = the held rows + world x quota
+    # gathered snapshots, masked greedy thinning back to no_keep, dense solve.  State and result travel as one packed
+    # buffer [COEFS | centers | their observations | status] (sections padded to 128 bytes), which is also what the
+    # collector broadcasts, so every rank can take the next round's refit duty.
+    @staticmethod
+    def pack_layout(n, d, m):
+        pad = lambda v: (v + 15) // 16 * 16
+        o_c = 0
+        o_x = o_c + pad((n + d + 1) * m)
+        o_y = o_x + pad(n * d)
+        o_s = o_y + pad(n * m)
+        return o_c, o_x, o_y, o_s, o_s + 16
+
+    def round_ready(self):
+        return (self.no_keep is not None and self._par.shape[0] == int(self.no_keep) and not self._new_par
+                and self.solver_type in ("direct", "nullspace"))
+
+    def pack_views(self, pack, n=None):
+        n = int(self.no_keep) if n is None else n
+        d, m = self.no_parameters, self.no_observations
+        o_c, o_x, o_y, o_s, _ = self.pack_layout(n, d, m)
+        return (pack[o_c:o_c + (n + d + 1) * m].view(n + d + 1, m), pack[o_x:o_x + n * d].view(n, d),
+                pack[o_y:o_y + n * m].view(n, m), pack[o_s:o_s + 16])
+
+    def adopt_pack(self, pack):
+        """Make a packed state (own refit or another rank's broadcast) this updater's state; -> DeviceModel."""
+        coefs, X, Y, _ = self.pack_views(pack)
+        self._par, self._obs = X, Y
+        self.no_processed = X.shape[0]
+        self._pack_cur = pack
+        return DeviceModel(L.MODEL_RBF, kernel_type=self.kernel_type, coefs=coefs, centers=X, d=self.no_parameters,
+                           m=self.no_observations)
+
+    def new_pack(self):
+        n, d, m = int(self.no_keep), self.no_parameters, self.no_observations
+        return torch.zeros((self.pack_layout(n, d, m)[4],), dtype=torch.float64, device="cuda")
+
+    def pack_from_state(self, model):
+        """The packed form of the current (general-path) state and model: entry into the fixed-shape rounds."""
+        pack = self.new_pack()
+        coefs, X, Y, _ = self.pack_views(pack)
+        coefs.copy_(model.coefs)
+        X.copy_(self._par)
+        Y.copy_(self._obs)
+        return pack
+
+    def update_round_device(self, gathered, world, quota, pack_cur, pack_out):
+        """One fixed-shape refit on the current stream.  gathered: [world x (quota + 1) x (d + m)] blocks of
+        sdb_snapshot_select.  pack_cur: the state to start from; pack_out receives the new state -- or a copy of pack_cur
+        when the solve failed (status[0] != 0: singular / not definite / non-finite coefficients / too few distinct rows),
+        so the chains never see a broken surrogate; the host reads the status later (`poll_status`)."""
+        n0, d, m = int(self.no_keep), self.no_parameters, self.no_observations
+        ncand = n0 + world * quota
+        rb = getattr(self, "_round_bufs", None)
+        if rb is None or rb["key"] != (ncand, n0):
+            rb = dict(key=(ncand, n0), X=torch.empty((ncand, d), dtype=torch.float64, device="cuda"),
+                      Y=torch.empty((ncand, m), dtype=torch.float64, device="cuda"),
+                      alive=torch.empty((ncand,), dtype=torch.uint8, device="cuda"),
+                      keep=torch.empty((ncand,), dtype=torch.uint8, device="cuda"),
+                      work=torch.empty((L.lib().sdb_rbf_thin_work(ncand),), dtype=torch.float64, device="cuda"),
+                      total=torch.zeros((1,), dtype=torch.int64, device="cuda"),
+                      count=torch.zeros((1,), dtype=torch.int32, device="cuda"),
+                      info=torch.zeros((4,), dtype=torch.int32, device="cuda"), new=self.new_pack())
+            self._round_bufs = rb
+        _, X0, Y0, _ = self.pack_views(pack_cur)
+        coefs, Xn, Yn, status = self.pack_views(rb["new"])
+        h, st = L.lib(), L.stream_handle()
+        L.check(h.sdb_round_candidates(L.ptr(X0), L.ptr(Y0), n0, L.ptr(gathered), world, quota, d, m, L.ptr(rb["X"]), L.ptr(rb["Y"]),
+                                       L.ptr(rb["alive"]), L.ptr(rb["total"]), st))
+        L.check(h.sdb_rbf_thin_masked(L.ptr(rb["X"]), ncand, d, n0, L.ptr(rb["alive"]), 0, L.ptr(rb["keep"]), L.ptr(rb["work"]), st))
+        L.check(h.sdb_rows_compact(L.ptr(rb["X"]), L.ptr(rb["Y"]), L.ptr(rb["keep"]), ncand, d, m, n0, L.ptr(Xn), L.ptr(Yn),
+                                   L.ptr(rb["count"]), st))
+        rb["info"].zero_()
+        self._solve_dense(Xn, Yn, coefs, n0, rb["info"])
+        bad = (rb["info"][0] != 0) | (rb["count"][0] != n0) | ~torch.isfinite(coefs).all()
+        status.zero_()
+        status[0] = bad.to(torch.float64)
+        status[1] = rb["info"][0].to(torch.float64)
+        status[2] = rb["count"][0].to(torch.float64)
+        status[3] = rb["total"][0].to(torch.float64)
+        torch.where(bad, pack_cur, rb["new"], out=pack_out)
+        pack_out[self.pack_layout(n0, d, m)[3]:].copy_(status)      # the status always describes THIS round
+        return pack_out
+
     def update(self):
         mo, n = self.update_device()
         self.last_info = self._info.cpu().numpy()
-        if self.solver_type in ("direct", "nullspace") and self.last_info[0] != 0:
-            raise np.linalg.LinAlgError("Singular matrix")          # what np.linalg.solve raises
         return [mo.coefs.cpu().numpy(), mo.centers.cpu().numpy()], n

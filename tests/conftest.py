@@ -10,12 +10,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
-    config.addinivalue_line("markers", "live_reference: needs /root/reference (build container only)")
+    config.addinivalue_line("markers", "live_reference: needs the reference modules (/root/reference, or oracle/_ref made by oracle.make_ref)")
 
 
 def pytest_collection_modifyitems(config, items):
-    have_ref = os.path.isfile("/root/reference/surrDAMH/modules/classes_SAMPLER.py")
-    skip_ref = pytest.mark.skip(reason="/root/reference not present on this machine")
+    from oracle import ref_import
+    have_ref = ref_import.available()
+    skip_ref = pytest.mark.skip(reason="reference modules not present on this machine (/root/reference or oracle/_ref)")
     for item in items:
         if "live_reference" in item.keywords and not have_ref:
             item.add_marker(skip_ref)

@@ -1,6 +1,8 @@
-"""CPU, world_size 2 over gloo: the collector's snapshot exchange (all-gather of ragged per-rank
-blocks in rank-major order, per-refit cap) and the coefficient broadcast -- the N>1 path of
-surrdamh_b200/collector.py with the GPU refit replaced by a recording stub (host logic only)."""
+"""CPU, world_size 2 over gloo: the collector's snapshot exchange (ONE all-gather of fixed-width per-rank
+blocks with the count in a header row, rank-major order, per-rank quota = snapshots_per_refit // world so that
+every rank's snapshots enter the refit), the model broadcast of the general path, and the fixed-shape path
+(packed state, ring of generations, rotating refit duty, one broadcast from the rank on duty) -- the N>1 logic of
+surrdamh_b200/collector.py with the GPU refit replaced by recording stubs (host logic only)."""
 import os
 import socket
 
@@ -50,7 +52,7 @@ def _worker(rank, world, port, kind, mode, cap, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from surrdamh_b200.collector import Collector
     d, m = 3, 2
-    upd = StubUpdater(d, m, kind) if (rank == 0 or mode == "replicated") else None
+    upd = StubUpdater(d, m, kind)
     col = Collector(upd, kind, d, m, rank=rank, world=world, snapshots_per_refit=cap, refit_mode=mode, device="cpu")
     col.model_factory = lambda k, coefs, extra: StubModel(coefs, extra if k == "rbf" else None, 0 if k == "rbf" else int(extra))
     res = []
@@ -84,13 +86,98 @@ def test_collector_exchange_world2(kind, mode, cap):
             assert (z0 is None) == (z1 is None)
             if z0 is not None:
                 assert np.array_equal(z0, z1)
-    # snapshot counts per refit: rank-major concatenation, capped
+    # snapshot counts per refit: rank-major concatenation, every rank capped at its quota = cap // world
     counts = [(5, 2), (0, 3), (4, 4)]
-    want = [min(a, cap or 99) + min(b, cap or 99) for a, b in counts]
-    if cap is not None:
-        want = [min(w, cap) for w in want]
+    quota = 99 if cap is None else max(1, cap // world)
+    want = [min(a, quota) + min(b, quota) for a, b in counts]
     assert [h[1] for h in r0[1]] == want
+    if kind == "rbf" and cap is not None:
+        centers = r0[0][0][2]                                        # BOTH ranks' snapshots enter the first refit
+        assert centers.shape[0] == want[0] and centers[0, 0] == 0.0 and centers[-1, 0] == 100.0
     if kind == "rbf" and cap is None:
         centers = r0[0][0][2]                                        # after round 0: 5 rows of rank 0 then 2 rows of rank 1
         assert centers.shape == (7, 3)
         assert np.array_equal(centers[:5, 0], np.arange(5.0)) and np.array_equal(centers[5:, 0], 100 + np.arange(2.0))
+
+
+
+class FixedStub:
+    """A CPU stand-in for the RBF updater's fixed-shape interface: state = the packed buffer; a 'refit' appends the sum of
+    the round's alive rows to a running checksum and records who did it."""
+    solver_type, round_failures = "direct", 0
+
+    def __init__(self, d, m, no_keep, rank):
+        self.d, self.m, self.no_keep, self.rank = d, m, no_keep, rank
+        self.done_by_me = []
+
+    def new_pack(self):
+        return torch.zeros((self.no_keep * (self.d + self.m + 1) + 32,), dtype=torch.float64)
+
+    def pack_views(self, pack):
+        n, d, m = self.no_keep, self.d, self.m
+        return (pack[:n].view(n, 1), pack[n:n + n * d].view(n, d), pack[n + n * d:n + n * d + n * m].view(n, m), pack[-16:])
+
+    def pack_from_state(self, model):
+        p = self.new_pack()
+        self.pack_views(p)[1].copy_(model.centers)
+        return p
+
+    def adopt_pack(self, pack):
+        coefs, X, Y, _ = self.pack_views(pack)
+        return StubModel(coefs, X)
+
+    def update_round_device(self, gathered, world, quota, cur, out):
+        g = gathered.view(world, quota + 1, self.d + self.m)
+        out.copy_(cur)
+        tot = 0.0
+        for r in range(world):
+            k = int(g[r, 0, 0])
+            tot += float(g[r, 1:1 + k].sum()) + 1000.0 * k
+        self.pack_views(out)[0][0, 0] += tot
+        self.pack_views(out)[3][3] = sum(int(g[r, 0, 0]) for r in range(world))
+        self.done_by_me.append(tot)
+        return out
+
+
+def _worker_fixed(rank, world, port, mode, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from surrdamh_b200.collector import Collector
+    d, m, n0 = 2, 1, 5
+    upd = FixedStub(d, m, n0, rank)
+    col = Collector(upd, "rbf", d, m, rank=rank, world=world, snapshots_per_refit=4, refit_mode=mode, device="cpu")
+    col.model_factory = lambda k, coefs, extra: StubModel(coefs, extra)
+    if rank == 0 or mode == "replicated":
+        col.model = StubModel(torch.zeros((n0 + d + 1, m), dtype=torch.float64), torch.arange(n0 * d, dtype=torch.float64).view(n0, d))
+    else:
+        col.model = StubModel(torch.zeros((n0 + d + 1, m), dtype=torch.float64), torch.zeros((n0, d), dtype=torch.float64))
+    sums = []
+    for rnd in range(5):
+        block = torch.zeros((col.quota + 1, d + m), dtype=torch.float64)
+        k = (rnd + rank) % (col.quota + 1)
+        block[0, 0] = k
+        block[1:1 + k] = 10.0 * rank + rnd + 1.0
+        gathered = col.gather(block)
+        if not col.fixed and col._can_go_fixed():
+            col._enter_fixed()
+        assert col.fixed
+        col._refit_fixed(gathered, rnd)
+        sums.append(float(col.model.coefs[0, 0]))
+    out[rank] = (sums, len(upd.done_by_me), col.model.centers.clone().numpy(), [s[4] for s in col.poll_status(wait=True)])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["broadcast", "rotate", "replicated"])
+def test_collector_fixed_shape_world2(mode):
+    world, port = 2, _free_port()
+    mgr = tmp.Manager()
+    out = mgr.dict()
+    tmp.spawn(_worker_fixed, args=(world, port, mode, out), nprocs=world, join=True)
+    (s0, n0, c0, t0), (s1, n1, c1, t1) = out[0], out[1]
+    assert s0 == s1                                         # the same surrogate on both ranks after every round
+    assert np.array_equal(c0, c1) and np.array_equal(c0.ravel(), np.arange(10.0))     # rank 0's state reached rank 1
+    assert all(b > a for a, b in zip(s0, s0[1:]))            # every round built on the previous generation
+    assert (n0, n1) == {"broadcast": (5, 0), "rotate": (3, 2), "replicated": (5, 5)}[mode]
+    want = [((r) % 3) + ((r + 1) % 3) for r in range(5)]     # snapshots offered per round: both ranks' counts
+    assert t0 == want and t1 == want
