@@ -135,7 +135,7 @@ def test_other_bench_shapes_full_size_cut_invariance(name):
     from surrdamh_b200.chains import ChainBlock, Proposal
     from surrdamh_b200.device import DeviceProblem
     w = bench.WORKLOADS[name]
-    _, sur, truth, _ = bench.build_models(w)
+    _, sur, truth = bench.build_models(w)
     prob = DeviceProblem(w["d"], **w["problem"])
     C_, steps = w["chains"], 5
 
