@@ -38,7 +38,11 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, mode, out):
+RBF_KW = dict(surrogate_type="rbf", surr_solver_parameters={"kernel_type": 1},
+              surr_updater_parameters={"kernel_type": 1, "solver_type": "nullspace", "no_keep": 300}, snapshots_per_refit=128)
+
+
+def _worker(rank, world, port, mode, out, extra=None, key=None):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
@@ -46,14 +50,16 @@ def _worker(rank, world, port, mode, out):
     from surrdamh_b200.configuration import Configuration
     from surrdamh_b200.sampler import LockstepSampler
     C_ = 256
-    conf = Configuration(4, conf=_conf_dict(refit_mode=mode))
+    conf = Configuration(4, conf=_conf_dict(refit_mode=mode, **(extra or {})))
     smp = LockstepSampler(conf, no_chains=C_, rank=rank, world=world, device=torch.device("cuda", rank))
     models = []
     for i, st in enumerate(conf.list_alg):
         smp.run_stage(i, st)
         models.append(smp.collector.model.coefs.cpu().numpy().copy())
-    out[(mode, rank)] = dict(u=smp.block.current_numpy(), counters=smp.block.counters_numpy(), models=models,
-                             history=list(smp.collector.history), degree=smp.collector.model.degree)
+    out[(key or mode, rank)] = dict(u=smp.block.current_numpy(), counters=smp.block.counters_numpy(), models=models,
+                                    history=list(smp.collector.history), degree=smp.collector.model.degree,
+                                    fixed=smp.collector.fixed, status=list(smp.collector.status_log),
+                                    centers=None if smp.collector.model.centers is None else smp.collector.model.centers.cpu().numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -76,6 +82,38 @@ def test_two_gpus_sharding_and_collector():
     # (frozen) stage from the same state on a single device and compare
     assert len(b0["history"]) == 2 + 4
     assert all(n <= 300 for _, n in b0["history"])
+
+
+def test_two_gpus_fixed_shape_rounds_all_modes_agree():
+    """RBF surrogate, 300 centers: once the center set is full the rounds run on the fixed-shape path (one all-gather, one
+    broadcast of the packed state, no host sync).  'broadcast' (rank 0 refits), 'rotate' (the duty alternates between the
+    ranks) and 'replicated' (both refit) must give bit-identical surrogates and chains on both ranks, and snapshots of
+    BOTH ranks enter every refit.  The asynchronous collector is deterministic across ranks as well."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 CUDA devices")
+    import torch.multiprocessing as tmp
+    mgr = tmp.Manager()
+    out = mgr.dict()
+    for mode in ("broadcast", "rotate", "replicated"):
+        tmp.spawn(_worker, args=(2, _free_port(), mode, out, RBF_KW, None), nprocs=2, join=True)
+    tmp.spawn(_worker, args=(2, _free_port(), "rotate", out, dict(RBF_KW, collector_async=True), "async"), nprocs=2, join=True)
+    ref = out[("broadcast", 0)]
+    assert ref["fixed"] and len(ref["history"]) == 2 + 4
+    for mode in ("broadcast", "rotate", "replicated"):
+        for rank in (0, 1):
+            o = out[(mode, rank)]
+            assert o["fixed"] and o["history"] == ref["history"]
+            for x, y in zip(o["models"], ref["models"]):
+                assert np.array_equal(x, y), (mode, rank)
+            assert np.array_equal(o["centers"], ref["centers"])
+            assert all(s[1] == 0 and s[3] == 300 for s in o["status"])      # every fixed-shape round succeeded, 300 rows kept
+        assert np.array_equal(out[(mode, 0)]["u"], ref["u"]) and np.array_equal(out[(mode, 1)]["u"], out[("broadcast", 1)]["u"])
+    # both ranks' snapshots entered the fixed-shape refits: 2 x 64 offered per round
+    assert all(s[4] == 128 for s in ref["status"])
+    a0, a1 = out[("async", 0)], out[("async", 1)]
+    for x, y in zip(a0["models"], a1["models"]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a0["centers"], a1["centers"]) and len(a0["history"]) == 2 + 4
 
 
 def test_sharding_independence_single_process():
