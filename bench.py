@@ -360,6 +360,8 @@ class Run:
         self.updater, self.sur, self.truth = build_models(w)
         self.prob = DeviceProblem(d, **w["problem"], device=dev)
         self.blk = ChainBlock(self.prob, C_, chain0=rank * C_, seed=2024, device=dev)
+        self.blk.surrogate_f32 = precision == "f32"
+        self.precision = precision
         self.prop = Proposal(d, w["proposal_std"], device=dev)
         self.col = self.acol = None
         self.lag = lag if collector == "async" else 0
@@ -539,6 +541,48 @@ def fp64_peaks(dev):
     return out
 
 
+def fp32_peak(dev):
+    import torch
+
+    from surrdamh_b200 import _lib as L
+    info = L.device_info()
+    pb, iters = info["sm_count"] * 8, 40000
+    pout = torch.empty((pb * 256,), dtype=torch.float32, device=dev)
+    L.check(L.lib().sdb_fp32_probe(iters, pb, L.ptr(pout), L.stream_handle()))
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    L.check(L.lib().sdb_fp32_probe(iters, pb, L.ptr(pout), L.stream_handle()))
+    p1.record()
+    p1.synchronize()
+    return pb * 256 * 8 * 2.0 * iters / (p0.elapsed_time(p1) * 1e-3) / 1e12
+
+
+def f32_decision_check(w, run, dev):
+    """One lockstep step from the SAME state with the same random numbers, surrogate in FP64 and in FP32: fraction of chains
+    whose stage-1 decision differs, and the relative difference of the surrogate log-posteriors."""
+    import torch
+
+    from surrdamh_b200.chains import ChainBlock, Trace
+    d, m, C_ = w["d"], w["m"], run.C
+    out = {}
+    for f32 in (False, True):
+        blk = ChainBlock(run.prob, C_, chain0=0, seed=77, device=dev)
+        blk.u.copy_(run.blk.u)
+        blk.surrogate_f32 = f32
+        blk.prepare("DAMH", run.state["sur"], run.truth)
+        tr = Trace(1, C_, d, m, dev, snapshots=False, full=True)
+        blk.run("DAMH", 1, run.prop, run.state["sur"], run.truth, trace=tr)
+        torch.cuda.synchronize(dev)
+        out[f32] = (tr.flags[0].cpu().numpy(), tr.pre[0].cpu().numpy())
+    p64, p32 = out[False][1], out[True][1]
+    rel = np.abs(p32 - p64) / np.maximum(1.0, np.abs(p64))
+    return {"stage1_decision_mismatch_rate": float(np.mean((out[False][0] != 0) != (out[True][0] != 0))),
+            "accept_mismatch_rate": float(np.mean((out[False][0] == 1) != (out[True][0] == 1))),
+            "pre_posterior_rel_diff_median": float(np.median(rel)), "pre_posterior_rel_diff_p99": float(np.percentile(rel, 99)),
+            "chains": int(C_), "note": "one step from the same state and random numbers; stage 2 uses the true posterior in FP64 "
+                                       "either way, so the sampled distribution is the exact posterior in both runs"}
+
+
 def kernel_name(w):
     if w["surrogate"] == "poly" and w["d"] == 2 and w["m"] == 1 and not os.environ.get("SDB_NO_LEAN"):
         return "chain_lean_kernel<%d,true>" % w["degree"]
@@ -564,6 +608,28 @@ def roofline_of(w, run, rec, peak_tf, peak3_tf, headline):
     return out
 
 
+def nccl_log_to_stderr(rank):
+    """NCCL's INFO log (communicator lines: nranks, rings, NVLS) must be visible, but stdout carries exactly one JSON
+    line: every rank logs into its own temporary file and copies it to stderr when the process ends."""
+    if os.environ.get("SDB_KEEP_NCCL_DEBUG"):
+        return
+    import atexit
+    path = os.path.join(tempfile.gettempdir(), "sdb_nccl_%d_rank%d.log" % (os.getpid(), rank))
+    os.environ["NCCL_DEBUG"] = "INFO"
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+    os.environ["NCCL_DEBUG_FILE"] = path
+
+    def dump():
+        try:
+            with open(path) as f:
+                sys.stderr.write(f.read())
+            sys.stderr.flush()
+            os.remove(path)
+        except OSError:
+            pass
+    atexit.register(dump)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -577,10 +643,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's log (communicator / ring lines at INFO) goes to stderr: stdout carries exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        nccl_log_to_stderr(rank)
         dist.init_process_group("nccl", device_id=dev)
     wname = args.workload
     w = dict(WORKLOADS[wname])
@@ -634,6 +697,28 @@ def run_ours(args):
                   "round_ms": float(np.mean(srec["rounds"])) if srec["rounds"] else None, "gpu_launches": srec["launches"]}
         del srun
 
+    # ---- the FP32-surrogate variant of the same workload (second line; the headline stays FP64) ---------------------------
+    fp32 = None
+    if w["surrogate"] == "rbf" and not args.no_extras:
+        frun = Run(w, w["chains"], rank, world, dev, collector, refit_mode, args.lag, precision="f32")
+        frec = frun.measure(max(10, args.steps // 2), 3, 2)
+        if rank == 0:
+            p32 = fp32_peak(dev)
+            per_point = flops_per_point(w, frun.sur)
+            k_ms = float(np.mean([k for k, _ in frec["kern"]]))
+            frac_sw = float(np.mean([1.0 if sw else 0.0 for _, sw in frec["kern"]]))
+            fl = float(frun.C) * (frun.K + frac_sw) * per_point
+            fp32 = {"surrogate_precision": "f32", "value": frec["value"], "unit": "chain steps/s", "ms_per_step": frec["ms_per_step"],
+                    "steps": frec["steps"], "e2e": frec["e2e"], "gpu_launches": frec["launches"],
+                    "roofline": {"bound": "fp32-pipe", "achieved": fl / (k_ms * 1e-3) / 1e12, "peak": p32, "unit": "TFLOP/s",
+                                 "frac": fl / (k_ms * 1e-3) / 1e12 / p32, "kernel": "chain_kernel<%d,%d,1>" % (w["d"], w["m"]),
+                                 "kernel_ms": k_ms, "flops_per_launch": fl,
+                                 "peak_source": "sdb_fp32_probe (8 independent FFMA chains/thread), measured live",
+                                 "note": "same algorithmic flop count as the FP64 kernel (SURVEY 8d: 3d+3+2m per pair); per pair "
+                                         "7 FP32 instructions + 1 MUFU.RSQ at d=2, m=1"},
+                    "vs_f64": f32_decision_check(w, frun, dev)}
+        del frun
+
     # ---- short records of the other single-GPU workloads ---------------------------------------------------------
     others = {}
     if world == 1 and not args.no_extras and wname == "cfg3" and not args.chains and not args.centers:
@@ -682,6 +767,8 @@ def run_ours(args):
                                  "round_ms": round_ms,
                                  "note": "n^3/3 flop of the Cholesky over the WHOLE collector round (exchange, thinning, build, "
                                          "solve), same live FP64 peak; at n = 4096 the round is latency-bound (DESIGN.md 4.2)"}
+    if fp32 is not None:
+        out["fp32_surrogate"] = fp32
     if strong is not None:
         out["strong"] = strong
     if others:

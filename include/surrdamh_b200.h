@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SDB_ABI_VERSION 1
+#define SDB_ABI_VERSION 2
 
 /* exported symbols (the library is built with -fvisibility=hidden) */
 #if defined(__GNUC__)
@@ -160,6 +160,11 @@ typedef struct sdb_chain_args {
     /* != 0: leave room on every SM for kernels of another stream (the collector's refit running concurrently):
      * at most one CTA of this kernel per SM (its shared-memory request is padded past half of the SM's) */
     int32_t coresident;
+    /* != 0 (additive, RBF surrogate only): the surrogate is evaluated in FP32 -- distances, kernel and the sum over
+     * centers on the FP32 pipe, linear tail and the log-posterior in FP64.  The reference evaluates in float64
+     * (surrogate_rbf.py:20-40); in a DAMH chain the surrogate only screens proposals, the accepted chain is corrected by
+     * the true posterior in stage 2 (classes_SAMPLER.py:193-195), so the sampled distribution does not depend on it. */
+    int32_t surrogate_f32;
 } sdb_chain_args;
 
 /* ---- library ------------------------------------------------------------------------- */
@@ -173,6 +178,12 @@ SDB_API int sdb_poly_eval(const double *d_points, int64_t N, int32_t d, int32_t 
                   void *stream);
 SDB_API int sdb_rbf_eval(const double *d_points, int64_t N, int32_t d, int32_t m, const sdb_model *model, double *d_out,
                  void *stream);
+
+/* The same contraction on the FP32 pipe (additive; Surrogate_apply(..., precision="f32")): centers relative to the first
+ * center and weights held in FP32 in shared memory (all of them: SDB_ERR_LIMIT when they do not fit), per-lane partial
+ * sums combined and the linear tail added in FP64.  |error| is about 1e-7 * sum_j |w_j phi_j|. */
+SDB_API int sdb_rbf_eval_f32(const double *d_points, int64_t N, int32_t d, int32_t m, const sdb_model *model, double *d_out,
+                     void *stream);
 
 /* ---- lockstep chains ------------------------------------------------------------------ */
 SDB_API int sdb_chain_run(const sdb_chain_args *args, void *stream);
@@ -276,6 +287,8 @@ SDB_API int64_t sdb_launch_count(int32_t reset);
 /* FP64 FMA throughput probe (roofline denominator of the FP64-pipe-bound kernels):
  * FLOPs = blocks * 256 * 8 * 2 * iters.  d_out: DEVICE doubles [blocks * 256]. */
 SDB_API int sdb_fp64_probe(int64_t iters, int32_t blocks, double *d_out, void *stream);
+/* FP32 FMA throughput (denominator for the FP32-surrogate chain kernel), same FLOP count.  d_out: DEVICE floats [blocks * 256]. */
+SDB_API int sdb_fp32_probe(int64_t iters, int32_t blocks, float *d_out, void *stream);
 /* Same FLOP count, but each FMA reads three distinct live registers (the operand pattern of real code). */
 SDB_API int sdb_fp64_probe3(int64_t iters, int32_t blocks, double *d_out, void *stream);
 

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_C", "libsurrdamh_b200.so")
 
 # ---- constants of the header ----------------------------------------------------------------
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, ERR_ARG, ERR_CUDA, ERR_LIMIT, ERR_SINGULAR = 0, 1, 2, 3, 4
 MAX_D, MAX_M, MAX_DEGREE = 32, 64, 10
 FLAG_PREREJECTED, FLAG_ACCEPTED, FLAG_REJECTED, FLAG_PENDING = 0, 1, 2, 3
@@ -54,7 +54,7 @@ class ChainArgs(C.Structure):
                 ("rng_kind", C.c_int32), ("seed", C.c_uint64), ("stream_id", C.c_uint32),
                 ("chain0", C.c_int64), ("step0", C.c_int64), ("z", _dp), ("uni", _dp),
                 ("flags", _dp), ("prop", _dp), ("post", _dp), ("pre", _dp),
-                ("snap_par", _dp), ("snap_obs", _dp), ("G_prop", _dp), ("pre_cur", _dp), ("coresident", C.c_int32)]
+                ("snap_par", _dp), ("snap_obs", _dp), ("G_prop", _dp), ("pre_cur", _dp), ("coresident", C.c_int32), ("surrogate_f32", C.c_int32)]
 
 
 class SdbError(RuntimeError):
@@ -73,6 +73,7 @@ _SIGNATURES = {
     "sdb_device_info": (C.c_int, [C.POINTER(C.c_int)] * 4),
     "sdb_poly_eval": (C.c_int, [_P, _L, _I, _I, C.POINTER(Model), _P, _P]),
     "sdb_rbf_eval": (C.c_int, [_P, _L, _I, _I, C.POINTER(Model), _P, _P]),
+    "sdb_rbf_eval_f32": (C.c_int, [_P, _L, _I, _I, C.POINTER(Model), _P, _P]),
     "sdb_chain_run": (C.c_int, [C.POINTER(ChainArgs), _P]),
     "sdb_chain_plan": (C.c_int, [C.POINTER(ChainArgs)] + [C.POINTER(C.c_int)] * 4),
     "sdb_philox_streams": (C.c_int, [C.c_uint64, C.c_uint32, _L, _L, _I, _I, _L, _P, _P, _P]),
@@ -97,6 +98,7 @@ _SIGNATURES = {
     "sdb_dgemm": (C.c_int, [_I, _I, _I, C.c_double, _P, _L, _L, _P, _L, _L, C.c_double, _P, _L, _I, _P, _P]),
     "sdb_launch_count": (C.c_int64, [_I]),
     "sdb_fp64_probe": (C.c_int, [_L, _I, _P, _P]),
+    "sdb_fp32_probe": (C.c_int, [_L, _I, _P, _P]),
     "sdb_fp64_probe3": (C.c_int, [_L, _I, _P, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)

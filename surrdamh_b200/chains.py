@@ -75,6 +75,7 @@ class ChainBlock:
         self.device = torch.device(device or "cuda")
         self.chain0, self.seed, self.stream_id = int(chain0), int(seed), int(stream_id)
         self.step0 = 0
+        self.surrogate_f32 = False           # additive: evaluate an RBF surrogate in FP32 (configuration key surrogate_precision)
         d, m, C_ = self.d, self.m, self.C
         if initial is None:                                   # prior mean (classes_SAMPLER.py:23-24)
             init = np.tile(problem.prior_mean_np.reshape(d, 1), (1, C_))
@@ -117,6 +118,7 @@ class ChainBlock:
         st.counters, st.moments = L.ptr(self.counters), L.ptr(self.moments)
         a.seed, a.stream_id, a.chain0, a.step0 = self.seed, self.stream_id, self.chain0, self.step0
         a.rng_kind = L.RNG_PHILOX
+        a.surrogate_f32 = int(bool(self.surrogate_f32) and surrogate is not None and surrogate.kind == L.MODEL_RBF)
         self._keep = (surrogate, truth)
         return a
 
@@ -146,6 +148,7 @@ class ChainBlock:
     # ---- K fused steps -------------------------------------------------------------------------
     def run(self, algorithm, n_steps, proposal, surrogate=None, truth=None, trace=None, streams=None,
             refresh_pre=False, lanes=0, stream=None, coresident=False):
+        """K fused steps.  The surrogate is evaluated in FP32 when `self.surrogate_f32` is set (RBF surrogates only)."""
         a = self._args(algorithm, L.PHASE_FUSED, surrogate, truth)
         a.coresident = int(bool(coresident))
         a.n_steps, a.lanes_per_chain, a.refresh_pre = int(n_steps), lanes, int(bool(refresh_pre))

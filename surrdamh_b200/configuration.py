@@ -19,6 +19,8 @@ ADDITIVE keys of this implementation (ignored by the reference, never renames):
   collector_async      true: the refit of block b runs on a side stream while the next blocks step; its
                        surrogate is used from block b + refit_lag + 1 on (default false: used from block b + 1)
   refit_lag            blocks of lag of the asynchronous collector (default 1)
+  surrogate_precision  'f64' (default, the reference's arithmetic) | 'f32': an RBF surrogate is evaluated on the FP32
+                       pipe inside the chain kernel (stage 1 only screens; stage 2 keeps the chain exact)
   drop_coincident      remove exactly coincident snapshots before an RBF solve (default true: lockstep chains
                        leaving a common start point emit identical snapshots, a singular system in the reference)
   seed                 Philox key of the chain RNG (default 0)
@@ -103,5 +105,8 @@ class Configuration:
         self.collector_async = bool(conf.get("collector_async", False))
         self.refit_lag = int(conf.get("refit_lag", 1))
         self.drop_coincident = bool(conf.get("drop_coincident", True))
+        self.surrogate_precision = conf.get("surrogate_precision", "f64")
+        if self.surrogate_precision not in ("f64", "f32"):
+            raise ValueError("surrogate_precision must be 'f64' or 'f32', got %r" % (self.surrogate_precision,))
         self.seed = int(conf.get("seed", 0))
         self.device_solver = bool(conf.get("device_solver", True))

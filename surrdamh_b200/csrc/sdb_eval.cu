@@ -203,3 +203,88 @@ extern "C" int sdb_rbf_eval(const double *d_points, int64_t N, int32_t d, int32_
     if (d == 4 && m == 3) return launch(rbf_eval_kernel<4, 3>);
     return launch(rbf_eval_kernel<0, 0>);
 }
+
+// ---------------------------------------------------------------------------------------------------
+// FP32 evaluation (additive: Surrogate_apply(..., precision="f32")): the arithmetic the chain kernel uses with
+// surrogate_f32, as a stand-alone kernel -- tables resident in shared memory as FP32, one point per lane, four
+// neighbouring lanes share their center loads.
+// ---------------------------------------------------------------------------------------------------
+template <int D, int M>
+__global__ void __launch_bounds__(256) rbf_eval32_kernel(const double *__restrict__ pts, int64_t N, int d, int m,
+                                                         const sdb_model mo, double *__restrict__ out) {
+    constexpr int DD = D ? D : SDB_MAX_D;
+    constexpr int UD = D ? D : 1;
+    constexpr int MM = M ? M : SDB_MAX_M;
+    constexpr int UM = M ? M : 1;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *p = smem;
+    const sdb_smodel32 s = sdb_stage_model32(mo, d, m, p);
+    const int64_t per_sweep = (int64_t)gridDim.x * blockDim.x;
+    const int64_t sweeps = (N + per_sweep - 1) / per_sweep;
+    for (int64_t sw = 0; sw < sweeps; ++sw) {        // whole warps stay converged: idle tail lanes shadow the last point
+        const int64_t i = sw * per_sweep + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const int64_t pc = i < N ? i : N - 1;
+        double x[DD], o[MM];
+#pragma unroll UD
+        for (int j = 0; j < DD; ++j)
+            if (j < d) x[j] = pts[pc * d + j];
+        if (D && M && D <= 4 && M <= 3) sdb_rbf32_point_team<D, M, 4>(s, d, m, x, o, 1);
+        else sdb_rbf32_point_team<D, M, 2>(s, d, m, x, o, 1);
+        if (i < N) {
+#pragma unroll UM
+            for (int k = 0; k < MM; ++k)
+                if (k < m) out[i * m + k] = o[k];
+        }
+    }
+}
+
+extern "C" int sdb_rbf_eval_f32(const double *d_points, int64_t N, int32_t d, int32_t m, const sdb_model *model,
+                                double *d_out, void *stream) {
+    SDB_CHECK_ARG(model && model->kind == SDB_MODEL_RBF, "sdb_rbf_eval_f32: model must be SDB_MODEL_RBF");
+    SDB_CHECK_ARG(d_points && d_out && model->coefs && model->centers, "sdb_rbf_eval_f32: NULL pointer");
+    SDB_CHECK_LIMIT(d >= 1 && d <= SDB_MAX_D && m >= 1 && m <= SDB_MAX_M, "sdb_rbf_eval_f32: d=%d m=%d outside limits", d, m);
+    SDB_CHECK_ARG(model->n_centers >= 1, "sdb_rbf_eval_f32: n_centers must be >= 1");
+    SDB_CHECK_ARG(model->kernel_type >= 0 && model->kernel_type <= 7, "sdb_rbf_eval_f32: kernel_type %d outside [0,7]",
+                  model->kernel_type);
+    if (N <= 0) return SDB_OK;
+    sdb_device_props dp;
+    int rc = sdb_get_device_props(&dp);
+    if (rc) return rc;
+    const size_t smem = sdb_model32_smem_bytes(*model, d, m);
+    SDB_CHECK_LIMIT(smem <= (size_t)dp.smem_optin, "sdb_rbf_eval_f32: FP32 tables need %zu B of shared memory (%d available)", smem,
+                    dp.smem_optin);
+    const int threads = 256;
+    int64_t blocks = (N + threads - 1) / threads;
+    if (blocks > (int64_t)dp.sm_count * 4) blocks = (int64_t)dp.sm_count * 4;
+    auto launch = [&](auto kern) -> int {
+        SDB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sdb_count_launch();
+        kern<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(d_points, N, d, m, *model, d_out);
+        SDB_CUDA(cudaGetLastError());
+        return SDB_OK;
+    };
+    if (d == 2 && m == 1) return launch(rbf_eval32_kernel<2, 1>);
+    if (d == 4 && m == 3) return launch(rbf_eval32_kernel<4, 3>);
+    return launch(rbf_eval32_kernel<0, 0>);
+}
+
+// FP32 FMA throughput probe (roofline denominator of the FP32-surrogate chain kernel): 8 independent FFMA chains per
+// thread; FLOPs = blocks * 256 * 8 * 2 * iters.  d_out: DEVICE floats [blocks * 256].
+__global__ void __launch_bounds__(256) fp32_probe_kernel(long long iters, float *out) {
+    float a0 = 1.0f + threadIdx.x * 1e-7f, a1 = a0 + 1e-3f, a2 = a0 + 2e-3f, a3 = a0 + 3e-3f, a4 = a0 + 4e-3f, a5 = a0 + 5e-3f,
+          a6 = a0 + 6e-3f, a7 = a0 + 7e-3f;
+    const float b = 0.9999999f, c = 1e-9f;
+    for (long long i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+        a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int sdb_fp32_probe(int64_t iters, int32_t blocks, float *d_out, void *stream) {
+    SDB_CHECK_ARG(iters >= 1 && blocks >= 1 && d_out, "sdb_fp32_probe: bad arguments");
+    sdb_count_launch();
+    fp32_probe_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((long long)iters, d_out);
+    SDB_CUDA(cudaGetLastError());
+    return SDB_OK;
+}

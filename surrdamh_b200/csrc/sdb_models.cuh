@@ -343,6 +343,293 @@ __device__ __forceinline__ void sdb_rbf_point_warp(const sdb_smodel &s, int d, i
 }
 
 // ---------------------------------------------------------------------------------------
+// FP32 evaluation of the RBF surrogate (additive option surrogate_precision = "f32"; the reference evaluates in
+// float64, surrogate_rbf.py:20-40).  Centers are stored relative to the first center (so that parameters far from the
+// origin do not lose the digits that matter: the difference), weights in FP32; distance, kernel and the sum over a
+// lane's centers run on the FP32 pipe with MUFU.RSQ / MUFU.EX2; the per-lane partial sums are combined and the
+// linear tail is added in FP64.  Per pair at d = 2, m = 1, cubic kernel: 7 FP32 instructions + 1 MUFU (the FP64
+// path: 11 FP64 instructions, each holding the issue port two cycles).  The result carries FP32 rounding of every
+// term: |error| <~ 1e-7 * sum_j |w_j phi_j|, i.e. 1e-4-accurate only while the expansion is not badly cancelling.
+// In a DAMH chain the surrogate only screens proposals (stage 1); stage 2 corrects with the true posterior, so the
+// chain targets the exact posterior whatever the surrogate's precision.
+// ---------------------------------------------------------------------------------------
+struct sdb_smodel32 {
+    int kernel_type, n_centers;
+    const float *centers;   // smem [n][d], relative to `shift`
+    const float *coefs;     // smem [n][m]
+    const double *tail;     // smem [(d+1)][m]: linear rows + constant row (FP64)
+    const double *shift;    // smem [d]
+};
+
+__host__ __device__ inline size_t sdb_model32_smem_bytes(const sdb_model &mo, int d, int m) {
+    return sdb_align16((size_t)mo.n_centers * d * 4) + sdb_align16((size_t)mo.n_centers * m * 4) +
+           sdb_align16((size_t)(d + 1) * m * 8) + sdb_align16((size_t)d * 8);
+}
+
+// All threads: convert the FP64 tables in global memory into the FP32 shared-memory layout (ends with __syncthreads).
+__device__ inline sdb_smodel32 sdb_stage_model32(const sdb_model &mo, int d, int m, unsigned char *&base) {
+    sdb_smodel32 s;
+    const int n = (int)mo.n_centers;
+    s.kernel_type = mo.kernel_type; s.n_centers = n;
+    float *c = (float *)base; base += sdb_align16((size_t)n * d * 4);
+    float *w = (float *)base; base += sdb_align16((size_t)n * m * 4);
+    double *t = (double *)base; base += sdb_align16((size_t)(d + 1) * m * 8);
+    double *sh = (double *)base; base += sdb_align16((size_t)d * 8);
+    for (int i = threadIdx.x; i < n * d; i += blockDim.x) c[i] = (float)(mo.centers[i] - mo.centers[i % d]);
+    for (int i = threadIdx.x; i < n * m; i += blockDim.x) w[i] = (float)mo.coefs[i];
+    for (int i = threadIdx.x; i < (d + 1) * m; i += blockDim.x) t[i] = mo.coefs[(size_t)n * m + i];
+    for (int i = threadIdx.x; i < d; i += blockDim.x) sh[i] = mo.centers[i];
+    __syncthreads();
+    s.centers = c; s.coefs = w; s.tail = t; s.shift = sh;
+    return s;
+}
+
+__device__ __forceinline__ float sdb_rsqrt32(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sdb_ex2_32(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+#define SDB_R2_FLOOR32 1e-30f   // keeps rsqrt away from 0 (r = 1e-15 for a coincident point)
+
+template <int KT>
+__device__ __forceinline__ float sdb_rbf_phi32(float s) {
+    if (KT == 4) return sdb_ex2_32(-1.4426950408889634f * s);
+    if (KT == 5) return sdb_rsqrt32(s + 1.0f);
+    const float r = s * sdb_rsqrt32(s);
+    if (KT == 1) return r * s;
+    if (KT == 2) return r * s * s;
+    if (KT == 3) return (r * s) * (s * s);
+    if (KT == 7) return (r * s * s) * (s * s);
+    return r;
+}
+
+template <int D, int M, int KT, int ST, int NP>
+__device__ __forceinline__ void sdb_rbf32_partialn_kt(const sdb_smodel32 &s, int d, int m, const float (*xs)[D ? D : SDB_MAX_D],
+                                                      float (*acc)[M ? M : SDB_MAX_M], int first, int stride_rt) {
+    constexpr int DD = D ? D : SDB_MAX_D;
+    constexpr int UD = D ? D : 1;
+    constexpr int MM = M ? M : SDB_MAX_M;
+    constexpr int UM = M ? M : 1;
+    const int n = s.n_centers;
+    const int stride = ST ? ST : stride_rt;
+    const float *c = s.centers + (size_t)first * d;
+    const float *w = s.coefs + (size_t)first * m;
+    const int cs = stride * d, ws = stride * m;
+#pragma unroll(8 / NP)
+    for (int i = first; i < n; i += stride, c += cs, w += ws) {
+        float r2[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) r2[p] = SDB_R2_FLOOR32;
+#pragma unroll UD
+        for (int j = 0; j < DD; ++j)
+            if (j < d) {
+                const float cj = c[j];
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const float df = cj - xs[p][j];
+                    r2[p] = fmaf(df, df, r2[p]);
+                }
+            }
+        float phi[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) phi[p] = sdb_rbf_phi32<KT>(r2[p]);
+#pragma unroll UM
+        for (int k = 0; k < MM; ++k)
+            if (k < m) {
+                const float wk = w[k];
+#pragma unroll
+                for (int p = 0; p < NP; ++p) acc[p][k] = fmaf(phi[p], wk, acc[p][k]);
+            }
+    }
+}
+
+template <int D, int M, int ST, int NP>
+__device__ __forceinline__ void sdb_rbf32_partialn_st(const sdb_smodel32 &s, int d, int m, const float (*xs)[D ? D : SDB_MAX_D],
+                                                      float (*acc)[M ? M : SDB_MAX_M], int first, int stride) {
+    switch (s.kernel_type) {
+        case 1: sdb_rbf32_partialn_kt<D, M, 1, ST, NP>(s, d, m, xs, acc, first, stride); break;
+        case 2: sdb_rbf32_partialn_kt<D, M, 2, ST, NP>(s, d, m, xs, acc, first, stride); break;
+        case 3: sdb_rbf32_partialn_kt<D, M, 3, ST, NP>(s, d, m, xs, acc, first, stride); break;
+        case 4: sdb_rbf32_partialn_kt<D, M, 4, ST, NP>(s, d, m, xs, acc, first, stride); break;
+        case 5: sdb_rbf32_partialn_kt<D, M, 5, ST, NP>(s, d, m, xs, acc, first, stride); break;
+        case 7: sdb_rbf32_partialn_kt<D, M, 7, ST, NP>(s, d, m, xs, acc, first, stride); break;
+        default: sdb_rbf32_partialn_kt<D, M, 0, ST, NP>(s, d, m, xs, acc, first, stride); break;
+    }
+}
+
+// The FP32 counterpart of sdb_rbf_point_team: NP neighbouring L-lane groups share their centers' loads.  Full warp, converged.
+template <int D, int M, int NP>
+__device__ __forceinline__ void sdb_rbf32_point_team(const sdb_smodel32 &s, int d, int m, const double *x, double *out, int L) {
+    constexpr int DD = D ? D : SDB_MAX_D;
+    constexpr int UD = D ? D : 1;
+    constexpr int MM = M ? M : SDB_MAX_M;
+    constexpr int UM = M ? M : 1;
+    const int team = (threadIdx.x & 31) & (NP * L - 1);
+    float xs[NP][DD], acc[NP][MM];
+#pragma unroll UD
+    for (int j = 0; j < DD; ++j)
+        if (j < d) {
+            const float xj = (float)(x[j] - s.shift[j]);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) xs[p][j] = p ? __shfl_xor_sync(0xffffffffu, xj, p * L) : xj;
+        }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+#pragma unroll UM
+        for (int k = 0; k < MM; ++k)
+            if (k < m) acc[p][k] = 0.0f;
+    }
+    if (NP * L == 2) sdb_rbf32_partialn_st<D, M, 2, NP>(s, d, m, xs, acc, team, 2);
+    else if (NP * L == 4) sdb_rbf32_partialn_st<D, M, 4, NP>(s, d, m, xs, acc, team, 4);
+    else sdb_rbf32_partialn_st<D, M, 0, NP>(s, d, m, xs, acc, team, NP * L);
+#pragma unroll UM
+    for (int k = 0; k < MM; ++k)
+        if (k < m) {
+            double t = (double)acc[0][k];
+#pragma unroll
+            for (int p = 1; p < NP; ++p) t += (double)__shfl_xor_sync(0xffffffffu, acc[p][k], p * L);
+            out[k] = t;
+        }
+    for (int off = L >> 1; off > 0; off >>= 1) {
+#pragma unroll UM
+        for (int k = 0; k < MM; ++k)
+            if (k < m) out[k] += sdb_shfl_xor(out[k], off);
+    }
+#pragma unroll UM
+    for (int k = 0; k < MM; ++k)
+        if (k < m) {
+            double t = 0.0;
+#pragma unroll UD
+            for (int j = 0; j < DD; ++j)
+                if (j < d) t = fma(x[j], s.tail[j * m + k], t);
+            out[k] += s.tail[d * m + k] + t;
+        }
+}
+
+// ---------------------------------------------------------------------------------------
+// Streamed RBF surrogate: the tables do not fit in shared memory (no_keep = None in the reference lets the center set
+// grow without bound, surrogate_rbf.py:43,97), so every evaluation streams them from L2 through a two-stage ring of
+// chunks filled by TMA bulk copies (full mbarriers; the stage is handed back by the CTA-wide barrier that follows its
+// use).  The ring simply keeps cycling over the table: the first chunks of the NEXT evaluation are already in flight
+// when an evaluation ends.  Chunks hold a multiple of 32 centers, so lane t of a team visits the same centers in the
+// same order as with resident tables: results are bit-identical to the resident path.
+// ---------------------------------------------------------------------------------------
+struct sdb_ring {
+    uint64_t *full;            // smem: full[0], full[1]
+    unsigned char *base;       // smem: 2 x (cbytes + wbytes)
+    size_t cbytes, wbytes;
+    int chunk, nchunks, n, kernel_type;
+    const double *g_centers, *g_coefs;   // global
+    const double *tail;        // smem [(d+1)][m]
+    long long total;           // chunks this CTA will consume over the whole launch
+    long long issued, consumed;
+    int phase_bits;
+};
+
+__host__ __device__ inline size_t sdb_ring_smem_bytes(int chunk, int d, int m) {
+    return 16 + sdb_align16((size_t)(d + 1) * m * 8) + 2 * (sdb_align16((size_t)chunk * d * 8) + sdb_align16((size_t)chunk * m * 8));
+}
+
+__device__ __forceinline__ void sdb_ring_issue(sdb_ring &r, int d, int m) {
+    // all threads call it: thread 0 drives the TMA, a few threads copy a (< 16 B) tail of the last chunk
+    const int ci = (int)(r.issued % r.nchunks), st = (int)(r.issued & 1);
+    const long long c0 = (long long)ci * r.chunk;
+    const int cn = (int)((r.n - c0) < r.chunk ? (r.n - c0) : r.chunk);
+    unsigned char *sc = r.base + (size_t)st * (r.cbytes + r.wbytes);
+    sdb_stage_table(sc, r.g_centers + c0 * d, (size_t)cn * d * 8, &r.full[st]);
+    sdb_stage_table(sc + r.cbytes, r.g_coefs + c0 * m, (size_t)cn * m * 8, &r.full[st]);
+    if (threadIdx.x == 0) sdb_mbar_arrive(&r.full[st]);
+    ++r.issued;
+}
+
+// All threads (barriers inside).  evals = number of surrogate evaluations this launch will make.
+__device__ inline sdb_ring sdb_ring_init(const sdb_model &mo, int d, int m, int chunk, long long evals, unsigned char *&base) {
+    sdb_ring r;
+    r.full = (uint64_t *)base; base += 16;
+    double *t = (double *)base; base += sdb_align16((size_t)(d + 1) * m * 8);
+    r.tail = t;
+    r.n = (int)mo.n_centers; r.kernel_type = mo.kernel_type;
+    r.chunk = chunk; r.nchunks = (r.n + chunk - 1) / chunk;
+    r.cbytes = sdb_align16((size_t)chunk * d * 8); r.wbytes = sdb_align16((size_t)chunk * m * 8);
+    r.base = base; base += 2 * (r.cbytes + r.wbytes);
+    r.g_centers = mo.centers; r.g_coefs = mo.coefs;
+    r.total = evals * r.nchunks; r.issued = 0; r.consumed = 0; r.phase_bits = 0;
+    if (threadIdx.x == 0) {
+        sdb_mbar_init(&r.full[0], 1);
+        sdb_mbar_init(&r.full[1], 1);
+        sdb_mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < (d + 1) * m; i += blockDim.x) t[i] = mo.coefs[(size_t)r.n * m + i];
+    __syncthreads();
+    while (r.issued < 2 && r.issued < r.total) sdb_ring_issue(r, d, m);
+    return r;
+}
+
+// One evaluation of every lane's point against the whole table.  Full CTA, converged (barriers inside).
+template <int D, int M, int NP>
+__device__ __forceinline__ void sdb_rbf_point_team_stream(sdb_ring &r, int d, int m, const double *x, double *out, int L) {
+    constexpr int DD = D ? D : SDB_MAX_D;
+    constexpr int UD = D ? D : 1;
+    constexpr int MM = M ? M : SDB_MAX_M;
+    constexpr int UM = M ? M : 1;
+    const int team = (threadIdx.x & 31) & (NP * L - 1);
+    double xs[NP][DD], acc[NP][MM];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+#pragma unroll UD
+        for (int j = 0; j < DD; ++j)
+            if (j < d) xs[p][j] = p ? sdb_shfl_xor(x[j], p * L) : x[j];
+#pragma unroll UM
+        for (int k = 0; k < MM; ++k)
+            if (k < m) acc[p][k] = 0.0;
+    }
+    for (int ci = 0; ci < r.nchunks; ++ci) {
+        const int st = (int)(r.consumed & 1);
+        sdb_mbar_wait(&r.full[st], (r.phase_bits >> st) & 1);
+        r.phase_bits ^= 1 << st;
+        const long long c0 = (long long)ci * r.chunk;
+        sdb_smodel s;
+        s.kind = SDB_MODEL_RBF; s.kernel_type = r.kernel_type;
+        s.n_centers = (int)((r.n - c0) < r.chunk ? (r.n - c0) : r.chunk);
+        s.centers = (const double *)(r.base + (size_t)st * (r.cbytes + r.wbytes));
+        s.coefs = (const double *)(r.base + (size_t)st * (r.cbytes + r.wbytes) + r.cbytes);
+        if (NP * L == 2) sdb_rbf_partialn_st<D, M, 2, NP>(s, d, m, xs, acc, team, 2);
+        else if (NP * L == 4) sdb_rbf_partialn_st<D, M, 4, NP>(s, d, m, xs, acc, team, 4);
+        else sdb_rbf_partialn_st<D, M, 0, NP>(s, d, m, xs, acc, team, NP * L);
+        ++r.consumed;
+        __syncthreads();      // every warp is done with stage st (and tail words of earlier issues are visible)
+        if (r.issued < r.total) sdb_ring_issue(r, d, m);
+    }
+#pragma unroll UM
+    for (int k = 0; k < MM; ++k)
+        if (k < m) {
+            double t = acc[0][k];
+#pragma unroll
+            for (int p = 1; p < NP; ++p) t += sdb_shfl_xor(acc[p][k], p * L);
+            out[k] = t;
+        }
+    for (int off = L >> 1; off > 0; off >>= 1) {
+#pragma unroll UM
+        for (int k = 0; k < MM; ++k)
+            if (k < m) out[k] += sdb_shfl_xor(out[k], off);
+    }
+#pragma unroll UM
+    for (int k = 0; k < MM; ++k)
+        if (k < m) {
+            double t = 0.0;
+#pragma unroll UD
+            for (int j = 0; j < DD; ++j)
+                if (j < d) t = fma(x[j], r.tail[j * m + k], t);
+            out[k] += r.tail[d * m + k] + t;
+        }
+}
+
+// ---------------------------------------------------------------------------------------
 // Toy model (examples/solvers/solver_examples.py:20-29), the reference's operation order with
 // separately rounded operations; bit-identical to numpy given the same exp().
 // ---------------------------------------------------------------------------------------

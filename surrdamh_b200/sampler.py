@@ -71,6 +71,7 @@ class LockstepSampler:
         self.chain0 = rank * self.C                               # global index of this rank's first chain
         self.block = ChainBlock(self.problem, self.C, initial=self._initial_samples(), chain0=self.chain0, seed=conf.seed,
                                 moments=moments, device=self.device)
+        self.block.surrogate_f32 = conf.surrogate_precision == "f32"
         self.collector = None
         if conf.use_surrogate:
             kt = conf.surr_updater_parameters.get("kernel_type", 0) if conf.surrogate_type == "rbf" else 0

@@ -21,10 +21,13 @@ from .surrogate_poly import _points
 
 
 class Surrogate_apply:
-    def __init__(self, no_parameters, no_observations, kernel_type=0):
+    def __init__(self, no_parameters, no_observations, kernel_type=0, precision="f64"):
         self.no_parameters = no_parameters
         self.no_observations = no_observations
         self.kernel_type = kernel_type
+        if precision not in ("f64", "f32"):
+            raise ValueError("precision must be 'f64' (the reference's arithmetic) or 'f32'")
+        self.precision = precision          # additive: 'f32' evaluates on the FP32 pipe (csrc/sdb_eval.cu, rbf_eval32_kernel)
         self._cache = (None, None)
 
     def device_model(self, SOL):
@@ -48,8 +51,8 @@ class Surrogate_apply:
         out = torch.empty((N, self.no_observations), dtype=torch.float64, device=pts.device)
         if N == 0:
             return out.cpu().numpy() if was_numpy else out
-        L.check(L.lib().sdb_rbf_eval(L.ptr(pts), N, self.no_parameters, self.no_observations, C.byref(mo.struct),
-                                     L.ptr(out), L.stream_handle(stream)))
+        fn = L.lib().sdb_rbf_eval_f32 if self.precision == "f32" else L.lib().sdb_rbf_eval
+        L.check(fn(L.ptr(pts), N, self.no_parameters, self.no_observations, C.byref(mo.struct), L.ptr(out), L.stream_handle(stream)))
         return out.cpu().numpy() if was_numpy else out
 
 
