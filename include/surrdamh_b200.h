@@ -165,6 +165,12 @@ typedef struct sdb_chain_args {
      * (surrogate_rbf.py:20-40); in a DAMH chain the surrogate only screens proposals, the accepted chain is corrected by
      * the true posterior in stage 2 (classes_SAMPLER.py:193-195), so the sampled distribution does not depend on it. */
     int32_t surrogate_f32;
+    /* Restrict the launch to the chains [chain_lo, chain_lo + chain_n) of the state (chain_n == 0: all).  The split
+     * phases use it to pipeline two halves of the chains against the host's solver pool: while the pool evaluates G for
+     * the survivors of one half, the other half is decided / proposed (process_SOLVER.py:60-106 keeps its solvers busy
+     * the same way by queueing requests).  Results do not depend on the split: the RNG is keyed by the global chain id. */
+    int64_t chain_lo;
+    int64_t chain_n;
 } sdb_chain_args;
 
 /* ---- library ------------------------------------------------------------------------- */

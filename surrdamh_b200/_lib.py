@@ -54,7 +54,8 @@ class ChainArgs(C.Structure):
                 ("rng_kind", C.c_int32), ("seed", C.c_uint64), ("stream_id", C.c_uint32),
                 ("chain0", C.c_int64), ("step0", C.c_int64), ("z", _dp), ("uni", _dp),
                 ("flags", _dp), ("prop", _dp), ("post", _dp), ("pre", _dp),
-                ("snap_par", _dp), ("snap_obs", _dp), ("G_prop", _dp), ("pre_cur", _dp), ("coresident", C.c_int32), ("surrogate_f32", C.c_int32)]
+                ("snap_par", _dp), ("snap_obs", _dp), ("G_prop", _dp), ("pre_cur", _dp), ("coresident", C.c_int32), ("surrogate_f32", C.c_int32),
+                ("chain_lo", C.c_int64), ("chain_n", C.c_int64)]
 
 
 class SdbError(RuntimeError):

@@ -161,16 +161,27 @@ class ChainBlock:
             self.moment_steps += int(n_steps)
 
     # ---- split path: host-evaluated G ----------------------------------------------------------
-    def propose(self, algorithm, proposal, surrogate, trace, streams=None, refresh_pre=False, stream=None):
+    def propose(self, algorithm, proposal, surrogate, trace, streams=None, refresh_pre=False, stream=None, chains=None, step0=None):
+        """chains = (lo, n): only the chains [lo, lo + n) take part (the pipelined split path); `step` bookkeeping is the
+        caller's then (decide() advances step0 only for full launches or when told to)."""
         a = self._args(algorithm, L.PHASE_PROPOSE, surrogate, None)
+        if chains is not None:
+            a.chain_lo, a.chain_n = int(chains[0]), int(chains[1])
         a.n_steps, a.refresh_pre = 1, int(bool(refresh_pre))
+        if step0 is not None:
+            a.step0 = int(step0)
         a.prop_kind, a.prop_scale = proposal.kind, L.ptr(proposal.scale)
         self._fill_rng(a, streams)
         self._fill_trace(a, trace, 1)
         self._launch(a, stream)
 
-    def decide(self, algorithm, proposal, surrogate, trace, G_prop, streams=None, stream=None):
+    def decide(self, algorithm, proposal, surrogate, trace, G_prop, streams=None, stream=None, chains=None, advance=True,
+               step0=None):
         a = self._args(algorithm, L.PHASE_DECIDE, surrogate, None)
+        if chains is not None:
+            a.chain_lo, a.chain_n = int(chains[0]), int(chains[1])
+        if step0 is not None:
+            a.step0 = int(step0)
         a.n_steps = 1
         a.prop_kind, a.prop_scale = proposal.kind, L.ptr(proposal.scale)
         self._fill_rng(a, streams)
@@ -178,9 +189,10 @@ class ChainBlock:
         self._G_prop = G_prop
         a.G_prop = L.ptr(G_prop)
         self._launch(a, stream)
-        self.step0 += 1
-        if self.moments is not None:
-            self.moment_steps += 1
+        if advance:
+            self.step0 += 1
+            if self.moments is not None:
+                self.moment_steps += 1
 
     def _fill_rng(self, a, streams):
         if streams is not None:

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(128) chain_lean_kernel(const sdb_chain_args a)
 static bool lean_applicable(const sdb_chain_args *a) {
     if (getenv("SDB_NO_LEAN")) return false;
     if (a->phase != SDB_PHASE_FUSED || a->problem.d != 2 || a->problem.m != 1 || a->problem.noise_full) return false;
-    if (a->lanes_per_chain > 1 || a->coresident) return false;
+    if (a->lanes_per_chain > 1 || a->coresident || a->chain_lo != 0 || a->chain_n != 0) return false;
     if (a->prop_kind != SDB_PROP_SHARED && a->prop_kind != SDB_PROP_PER_CHAIN) return false;
     if (a->truth.kind != SDB_MODEL_TOY && a->truth.kind != SDB_MODEL_ZERO) return false;
     if (a->algorithm == SDB_ALG_DAMH)
@@ -250,6 +250,8 @@ static int validate(const sdb_chain_args *a) {
     SDB_CHECK_LIMIT(p.d >= 1 && p.d <= SDB_MAX_D, "no_parameters %d outside [1,%d]", p.d, SDB_MAX_D);
     SDB_CHECK_LIMIT(p.m >= 1 && p.m <= SDB_MAX_M, "no_observations %d outside [1,%d]", p.m, SDB_MAX_M);
     SDB_CHECK_ARG(a->state.n_chains >= 1, "n_chains must be >= 1");
+    SDB_CHECK_ARG(a->chain_lo >= 0 && a->chain_n >= 0 && a->chain_lo < a->state.n_chains, "chain range [%lld, +%lld) outside the %lld chains",
+                  (long long)a->chain_lo, (long long)a->chain_n, (long long)a->state.n_chains);
     SDB_CHECK_ARG(a->state.u && a->state.G_u && a->state.post_u && a->state.pre_u && a->state.counters,
                   "chain state pointers must not be NULL");
     SDB_CHECK_ARG(p.prior_mean && p.prior_scale && p.obs && p.noise_scale, "problem pointers must not be NULL");
@@ -335,7 +337,8 @@ static int plan(const sdb_chain_args *a, int *L_out, int *threads_out, int *bloc
                     smem, dp.smem_optin);
     if (mode_out) *mode_out = mode;
     if (chunk_out) *chunk_out = chunk;
-    const int64_t C = a->state.n_chains;
+    int64_t C = a->state.n_chains;             // chains this launch steps
+    if (a->chain_n > 0) C = a->chain_lo + a->chain_n < C ? a->chain_n : C - a->chain_lo;
     const bool splittable = a->surrogate.kind == SDB_MODEL_RBF;  // only the RBF pair loop is split across lanes
     int L = a->lanes_per_chain;
     if (L <= 0) {

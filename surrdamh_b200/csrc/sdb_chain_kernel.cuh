@@ -130,10 +130,11 @@ __global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, c
 
     // ---- chain ownership ---------------------------------------------------------------------
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t grp = gtid / L;
+    const int64_t c_hi = a.chain_n > 0 ? (a.chain_lo + a.chain_n < C ? a.chain_lo + a.chain_n : C) : C;   // chains [chain_lo, c_hi)
+    const int64_t grp = a.chain_lo + gtid / L;
     const int sub = (int)(gtid % L);
-    const bool active = grp < C;
-    const int64_t c = active ? grp : (C - 1);  // idle tail lanes shadow the last chain, stores masked
+    const bool active = grp < c_hi;
+    const int64_t c = active ? grp : (c_hi - 1);  // idle tail lanes shadow the last chain, stores masked
     const bool writer = active && sub == 0;
     const uint64_t gchain = (uint64_t)(a.chain0 + c);
     const bool damh = a.algorithm == SDB_ALG_DAMH;

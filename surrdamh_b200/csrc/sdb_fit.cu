@@ -270,6 +270,24 @@ __device__ __forceinline__ double ref_distance(const double *__restrict__ xi, co
     return __dsqrt_rn(ref_sumsq(xi, xj, d));
 }
 
+// Running "smallest distance, ties -> the earlier index" over a sequence visited in ascending index order, WITHOUT a square
+// root per candidate: squared distances are compared, and only when a new one is smaller by less than 1e-15 (relative) --
+// i.e. when the two correctly rounded roots could coincide -- are the roots themselves compared.  sqrt is monotone, so
+// the winner is exactly the one the reference's arg-min over rounded distances (surrogate_rbf.py:98-103) picks.
+// The FP64 pipe of one SM is what bounds a rescan: 5 instructions per candidate instead of ~20 with the root.
+struct sq_best {
+    double sq;
+    int j;
+    __device__ __forceinline__ void init() { sq = DBL_MAX; j = INT_MAX; }
+    __device__ __forceinline__ void offer(double s, int idx) {
+        if (s < sq) {       // rarely true after the first few candidates: the band test costs nothing on the common path
+            if (s >= sq * (1.0 - 1e-15) && !(__dsqrt_rn(s) < __dsqrt_rn(sq))) return;   // same rounded distance: the earlier index stays
+            sq = s; j = idx;
+        }
+    }
+    __device__ __forceinline__ double dist() const { return j == INT_MAX ? DBL_MAX : __dsqrt_rn(sq); }
+};
+
 __device__ __forceinline__ double ref_phi(double r, int kt) {
     switch (kt) {
         case 1: return r * r * r;
@@ -426,13 +444,14 @@ __global__ void __launch_bounds__(256) thin_nearest_kernel(const double *__restr
         if (lane == 0) { nn_dist[row] = DBL_MAX; nn_idx[row] = INT_MAX; }
         return;
     }
-    double best = DBL_MAX;
-    int bj = INT_MAX;
+    sq_best sb;
+    sb.init();
     for (int j = lane; j < n; j += 32) {
         if (j == row || (alive && !alive[j])) continue;
-        const double r = ref_distance(X + (size_t)row * d, X + (size_t)j * d, d);
-        if (r < best) { best = r; bj = j; }   // j ascending per lane: first minimum kept
+        sb.offer(ref_sumsq(X + (size_t)row * d, X + (size_t)j * d, d), j);   // j ascending per lane: first minimum kept
     }
+    double best = sb.dist();
+    int bj = sb.j;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, best, off);
@@ -530,13 +549,14 @@ __global__ void __launch_bounds__(1024, 1) thin_remove_kernel(const double *__re
             const int cnt = again ? 1024 : found;
             for (int t = 0; t < cnt; ++t) {   // the whole CTA scans one row at a time
                 const int row = todo[t];
-                double b = DBL_MAX;
-                int bj = INT_MAX;
+                sq_best sb;
+                sb.init();
                 for (int j = tid; j < n; j += blockDim.x) {
                     if (j == row || !keep[j]) continue;
-                    const double r = ref_distance(X + (size_t)row * d, X + (size_t)j * d, d);
-                    if (r < b) { b = r; bj = j; }
+                    sb.offer(ref_sumsq(X + (size_t)row * d, X + (size_t)j * d, d), j);
                 }
+                double b = sb.dist();
+                int bj = sb.j;
                 block_argmin(b, bj, rv, rr);
                 if (tid == 0) { nn_dist[row] = b; nn_idx[row] = bj; }
             }
@@ -685,8 +705,8 @@ __global__ void __maxnreg__(KT <= 9 ? 72 : 128) thin_remove_fast_kernel(const do
 #pragma unroll
                     for (int k = 0; k < D; ++k) xr[k] = Xs[(size_t)row * D + k];
                 }
-                double b = INF;
-                int bj = INT_MAX;
+                sq_best sb;
+                sb.init();
 #pragma unroll 4
                 for (int j = tid; j < n; j += THF_T) {
                     double sq = 0.0;
@@ -703,11 +723,10 @@ __global__ void __maxnreg__(KT <= 9 ? 72 : 128) thin_remove_fast_kernel(const do
                     } else {
                         sq = ref_sumsq(Xs + (size_t)row * d, Xs + (size_t)j * d, d);
                     }
-                    const double r = __dsqrt_rn(sq);
-                    const bool lt = r < b && j != row;
-                    b = lt ? r : b;
-                    bj = lt ? j : bj;
+                    if (j != row) sb.offer(sq, j);
                 }
+                double b = sb.j == INT_MAX ? INF : __dsqrt_rn(sb.sq);
+                int bj = sb.j;
                 thf_argmin(b, bj, R, buf);
                 buf ^= 1;
                 {

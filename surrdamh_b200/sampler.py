@@ -88,6 +88,7 @@ class LockstepSampler:
         self.global_step = 0
         self.results = []
         self.no_G_calls_host = 0
+        self.overlap_stats = {"queued_while_busy": 0}     # split path: batches queued on the pool while another was in flight
 
     # process_SAMPLER.py:48-52 -- LHS rows `rank` of an N-point design, or the prior mean
     def _initial_samples(self):
@@ -223,27 +224,71 @@ class LockstepSampler:
         return up
 
     def _run_split(self, kind, K, prop, surrogate, trace, strm, swapped, collects):
-        """K steps with the true model evaluated by the host plugin (one step per kernel pair)."""
-        blk = self.block
-        one = Trace(1, self.C, self.d, self.m, self.device, snapshots=collects)
-        for k in range(K):
-            st = None if strm is None else (strm[0][k:k + 1].contiguous(), strm[1][k:k + 1].contiguous())
-            blk.propose(kind, prop, surrogate, one, streams=st, refresh_pre=swapped and k == 0)
-            flags = one.flags[0].cpu().numpy()
+        """K steps with the true model evaluated by the host plugin (one PROPOSE / DECIDE kernel pair per step).
+
+        With a solver pool the chains are worked in two halves, software-pipelined against the pool: while the workers
+        evaluate G for the stage-1 survivors of half A, the GPU decides half B's previous step and proposes its next one,
+        whose survivors are queued behind A's -- the solvers never wait for the GPU or the copies (the reference's pool
+        keeps its solvers busy by queueing the samplers' requests, process_SOLVER.py:60-106).  Every chain still takes
+        its steps in order with its own (chain, step) random numbers, so the result is identical to the unsplit loop."""
+        blk, C_ = self.block, self.C
+        one = Trace(1, C_, self.d, self.m, self.device, snapshots=collects)
+        Gd = torch.zeros((self.m, C_), dtype=torch.float64, device=self.device)
+        halves = [(0, C_)] if (self.pool is None or C_ < 2) else [(0, C_ // 2), (C_ // 2, C_ - C_ // 2)]
+        base = blk.step0
+        inflight = {}                      # half index -> (step k, chain indices of the survivors, handle | G array)
+
+        def stream_of(k):
+            return None if strm is None else (strm[0][k:k + 1].contiguous(), strm[1][k:k + 1].contiguous())
+
+        def propose(h, k):
+            lo, n = halves[h]
+            blk.propose(kind, prop, surrogate, one, streams=stream_of(k), refresh_pre=swapped and k == 0, chains=(lo, n),
+                        step0=base + k)
+            flags = one.flags[0, lo:lo + n].cpu().numpy()
             idx = np.nonzero(flags == L.FLAG_PENDING)[0]
-            G = np.zeros((self.C, self.m))
+            if idx.size == 0:
+                inflight[h] = (k, idx, np.empty((0, self.m)))
+                return
+            props = one.prop[0][:, lo:lo + n].cpu().numpy().T[idx]
+            if self.pool is not None:
+                if any(isinstance(v[2], tuple) for v in inflight.values()):
+                    self.overlap_stats["queued_while_busy"] += 1        # the other half's G is still being evaluated
+                inflight[h] = (k, idx, ("pool", self.pool.submit(props)))
+                self.no_G_calls_host += props.shape[0]
+            else:
+                inflight[h] = (k, idx, self._host_G(props))
+
+        def decide(h):
+            lo, n = halves[h]
+            k, idx, G = inflight.pop(h)
+            if isinstance(G, tuple):
+                G = self.pool.collect(G[1]).reshape(idx.size, self.m)
             if idx.size:
-                props = one.prop[0].cpu().numpy().T
-                G[idx] = self._host_G(props[idx])
-            Gd = L.dev(np.ascontiguousarray(G.T), device=self.device)
-            blk.decide(kind, prop, surrogate, one, Gd, streams=st)
+                full = np.zeros((n, self.m))
+                full[idx] = G
+                Gd[:, lo:lo + n] = L.dev(np.ascontiguousarray(full.T), device=self.device)
+            blk.decide(kind, prop, surrogate, one, Gd, streams=stream_of(k), chains=(lo, n), advance=False, step0=base + k)
             if trace is not None:
-                trace.flags[k] = one.flags[0]
+                sl = slice(lo, lo + n)
+                trace.flags[k, sl] = one.flags[0, sl]
                 if trace.prop is not None:
-                    trace.prop[k], trace.post[k], trace.pre[k] = one.prop[0], one.post[0], one.pre[0]
-                    trace.pre_cur[k] = one.pre_cur[0]
+                    trace.prop[k, :, sl], trace.post[k, sl], trace.pre[k, sl] = one.prop[0][:, sl], one.post[0, sl], one.pre[0, sl]
+                    trace.pre_cur[k, sl] = one.pre_cur[0, sl]
                 if collects:
-                    trace.snap_par[k], trace.snap_obs[k] = one.snap_par[0], one.snap_obs[0]
+                    trace.snap_par[k, :, sl], trace.snap_obs[k, :, sl] = one.snap_par[0][:, sl], one.snap_obs[0][:, sl]
+            return k
+
+        for h in range(len(halves)):
+            propose(h, 0)
+        for k in range(K):
+            for h in range(len(halves)):
+                decide(h)
+                if k + 1 < K:
+                    propose(h, k + 1)
+        blk.step0 = base + K
+        if blk.moments is not None:
+            blk.moment_steps += K
 
     def run(self):
         """All stages of samplers_list (process_SAMPLER.py:53-88)."""

@@ -3,8 +3,10 @@
 Counterpart of the reference's solver pool: surrDAMH/process_SOLVER.py:60-106 queues the samplers' requests and
 dispatches them to `no_solvers` spawned solver processes (process_CHILD.py:37-50), each of which owns one instance of
 the user's solver class and answers set_parameters / get_observations.  With lockstep chains the requests of a step
-arrive together (the proposals that passed the surrogate test), so the pool is a plain scatter / gather: the batch is
-split over the workers, every worker calls the reference plugin interface once per parameter vector.
+arrive together (the proposals that passed the surrogate test): a batch is split over the workers, every worker
+calls the reference plugin interface once per parameter vector.  Batches are queued asynchronously (`submit` /
+`collect`), so the sampler can keep the pool busy with one half of the chains while the GPU decides and re-proposes the
+other half (sampler.LockstepSampler._run_split).
 
 Workers are separate processes (the plugin may not be thread-safe and usually is not GIL-friendly); each imports the
 solver module from `solver_module_path` itself, exactly as process_CHILD.py:13-25 does.
@@ -52,18 +54,29 @@ class HostSolverPool:
         return cls(conf.no_full_solvers, c["solver_module_path"], c["solver_module_name"], c["solver_init_name"],
                    c.get("solver_parameters", {}), c.get("paths_to_append", []))
 
-    def evaluate(self, params):
-        """params [n x d] -> G [n x m], rows in the order given."""
+    def submit(self, params):
+        """Queue params [n x d] on the workers and return at once (process_SOLVER.py:60-106 queues the samplers'
+        requests the same way); `collect` waits for the answers.  Several batches may be in flight."""
         params = np.asarray(params, dtype=float)
         n = params.shape[0]
         if n == 0:
-            return np.empty((0, 0))
+            return None
         k = min(self.no_solvers, n)
         bounds = np.linspace(0, n, k + 1).astype(int)
         chunks = [params[bounds[i]:bounds[i + 1]] for i in range(k)]
-        parts = self.pool.map(_evaluate_chunk, chunks)
         self.no_calls += n
-        return np.vstack(parts)
+        return self.pool.map_async(_evaluate_chunk, chunks)
+
+    @staticmethod
+    def collect(handle):
+        """-> G [n x m], rows in the order submitted."""
+        if handle is None:
+            return np.empty((0, 0))
+        return np.vstack(handle.get())
+
+    def evaluate(self, params):
+        """params [n x d] -> G [n x m], rows in the order given."""
+        return self.collect(self.submit(params))
 
     def close(self):
         self.pool.close()
