@@ -11,7 +11,9 @@ surrogate_is_updated=true: every 64 lockstep steps each rank picks its share of 
 (greedy thinning back to 4096 centers, saddle-point system build, dense direct solve: null-space
 projection + Cholesky; `--solver direct` selects the LU with partial pivoting that mirrors the
 reference's solver_type 'direct'), ONE broadcast of the packed state hands the new surrogate to
-every rank.  The headline is WEAK scaling (65536 chains per GPU); with N > 1 the same line carries
+every rank.  The collector is asynchronous, as the reference's separate COLLECTOR process is: round b runs on a
+side stream beside block b+1 and its surrogate is used from block b+2 (a deterministic lag; `--collector sync`
+refits between blocks).  The headline is WEAK scaling (65536 chains per GPU); with N > 1 the same line carries
 the STRONG-scaling record (65536 chains split evenly over the N GPUs) under "strong".
     cfg2: 4096 chains, frozen polynomial surrogate (degree 5)        (BASELINE.json configs[1])
     cfg5: 131072 chains/GPU, d=4, m=3, frozen cubic RBF 500 centers, frozen 2000-center RBF as G
@@ -65,6 +67,7 @@ def static_config(wname, w):
             "poly_degree": w.get("degree"), "surrogate_is_updated": bool(w["updated"]),
             "refit_every": w["block"] if w["updated"] else None,
             "snapshots_per_refit": w.get("snapshots_per_refit") if w["updated"] else None,
+            "collector": "asynchronous, deterministic lag of one block (the reference's collector is a separate process)" if w["updated"] else None,
             "proposal_std": w["proposal_std"], "true_model": w["truth"],
             "l2": "GPU arm: 256 MiB flush write before every bench step, inside the timed region"}
 
@@ -653,7 +656,7 @@ def run_ours(args):
         w["centers"] = args.centers
     if args.solver and w["surrogate"] == "rbf":
         w["solver_type"] = args.solver
-    collector = args.collector or "sync"
+    collector = args.collector or "async"
     refit_mode = args.refit_mode or "broadcast"
 
     # ---- CPU baseline (rank 0, N == 1 only), before the timed GPU region -------------------------------
@@ -835,7 +838,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling record (N > 1) and the cfg2 / cfg5 records (N = 1)")
     ap.add_argument("--collector", default="", choices=["", "sync", "async"],
-                    help="async: the collector round runs on a side stream beside the next block(s)")
+                    help="async (default): the collector round runs on a side stream beside the next block and its surrogate is "
+                         "used from block b+2 on, like the reference's separate collector process; sync: between blocks")
     ap.add_argument("--refit-mode", default="", choices=["", "broadcast", "rotate", "replicated"])
     ap.add_argument("--lag", type=int, default=1, help="blocks of lag of the asynchronous collector")
     ap.add_argument("--profile", type=int, default=0, help="run this many bench steps inside cudaProfilerStart/Stop and exit")
