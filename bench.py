@@ -350,7 +350,7 @@ def build_models(w):
 class Run:
     """One measured configuration on this rank: C_ chains of workload w, synchronous or asynchronous collector."""
 
-    def __init__(self, w, C_, rank, world, dev, collector="sync", refit_mode="broadcast", lag=1, precision="f64"):
+    def __init__(self, w, C_, rank, world, dev, collector="sync", refit_mode="broadcast", lag=1, precision="f64", reserve_sms=16):
         import torch
 
         from surrdamh_b200.chains import ChainBlock, Proposal, Trace
@@ -368,6 +368,7 @@ class Run:
         self.prop = Proposal(d, w["proposal_std"], device=dev)
         self.col = self.acol = None
         self.lag = lag if collector == "async" else 0
+        self.reserve_sms = reserve_sms if collector == "async" else 0
         if w["updated"]:
             self.col = Collector(self.updater, "rbf", d, m, kernel_type=w["kernel_type"], rank=rank, world=world,
                                  snapshots_per_refit=w["snapshots_per_refit"], refit_mode=refit_mode, device=dev)
@@ -406,7 +407,7 @@ class Run:
             blk.prepare("DAMH", st["sur"], self.truth)                        # G(u), posteriors of the uploaded samples
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        blk.run("DAMH", K, self.prop, st["sur"], self.truth, trace=trace, refresh_pre=st["swapped"], coresident=acol is not None)
+        blk.run("DAMH", K, self.prop, st["sur"], self.truth, trace=trace, refresh_pre=st["swapped"], coresident=self.reserve_sms)
         e1.record()
         if timed:
             self.kern_ev.append((e0, e1, st["swapped"]))
@@ -668,7 +669,7 @@ def run_ours(args):
             cpu["refit_s"] = fit_s
             cpu["refit_note"] = "one full Surrogate_update.update() of the same CPU implementation at n = %d (solver_type 'direct', all host threads)" % WORKLOADS[wname]["centers"]
 
-    run = Run(w, w["chains"], rank, world, dev, collector, refit_mode, args.lag)
+    run = Run(w, w["chains"], rank, world, dev, collector, refit_mode, args.lag, reserve_sms=args.reserve_sms)
     if args.profile:
         run.warmup(max(args.warmup, 3))
         torch.cuda.synchronize(dev)
@@ -692,7 +693,7 @@ def run_ours(args):
     # ---- strong scaling: the same 65536 chains split evenly over the ranks ------------------------------------
     strong = None
     if world > 1 and w["updated"] and not args.no_extras and w["chains"] % world == 0:
-        srun = Run(w, w["chains"] // world, rank, world, dev, collector, refit_mode, args.lag)
+        srun = Run(w, w["chains"] // world, rank, world, dev, collector, refit_mode, args.lag, reserve_sms=args.reserve_sms)
         srec = srun.measure(args.steps, args.warmup, e2e_steps)
         strong = {"scaling": "strong", "chains_total": w["chains"], "chains_per_gpu": w["chains"] // world, "value": srec["value"],
                   "unit": "chain steps/s", "ms_per_step": srec["ms_per_step"], "e2e": srec["e2e"],
@@ -703,7 +704,7 @@ def run_ours(args):
     # ---- the FP32-surrogate variant of the same workload (second line; the headline stays FP64) ---------------------------
     fp32 = None
     if w["surrogate"] == "rbf" and not args.no_extras:
-        frun = Run(w, w["chains"], rank, world, dev, collector, refit_mode, args.lag, precision="f32")
+        frun = Run(w, w["chains"], rank, world, dev, collector, refit_mode, args.lag, precision="f32", reserve_sms=args.reserve_sms)
         frec = frun.measure(max(10, args.steps // 2), 3, 2)
         if rank == 0:
             p32 = fp32_peak(dev)
@@ -759,7 +760,7 @@ def run_ours(args):
         n_c = w["centers"]
         round_ms = float(np.mean(rec["rounds"]))
         flop = n_c ** 3 / 3.0
-        out["collector"] = {"mode": collector, "refit_mode": refit_mode, "lag_blocks": run.lag, "round_ms": round_ms,
+        out["collector"] = {"mode": collector, "refit_mode": refit_mode, "lag_blocks": run.lag, "reserved_sms": run.reserve_sms, "round_ms": round_ms,
                             "rounds": len(rec["rounds"]), "refit_failures": rec["refit_failures"], "solver": w.get("solver_type"),
                             "system_size": n_c + d + 1,
                             "what": "select + all-gather + masked thinning + system build + dense solve + broadcast; "
@@ -842,6 +843,7 @@ def main():
                          "used from block b+2 on, like the reference's separate collector process; sync: between blocks")
     ap.add_argument("--refit-mode", default="", choices=["", "broadcast", "rotate", "replicated"])
     ap.add_argument("--lag", type=int, default=1, help="blocks of lag of the asynchronous collector")
+    ap.add_argument("--reserve-sms", type=int, default=16, help="SMs the chain kernel leaves to the asynchronous collector's kernels")
     ap.add_argument("--profile", type=int, default=0, help="run this many bench steps inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
     if args.impl == "reference":

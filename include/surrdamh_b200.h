@@ -126,7 +126,9 @@ typedef struct sdb_chain_args {
     int32_t algorithm; /* SDB_ALG_* */
     int32_t phase;     /* SDB_PHASE_* */
     int32_t n_steps;   /* K lockstep steps in this launch (1 for the split phases) */
-    int32_t lanes_per_chain; /* 1,2,4,8,16 or 32 threads cooperating on one chain; 0 = library picks */
+    int32_t lanes_per_chain; /* 1,2,4,8,16 or 32 threads cooperating on one chain; 0 = library picks (with an RBF
+                              * surrogate: warp-owned chains -- a warp owns up to 32 chains, one per lane, and all 32 lanes
+                              * split the centers of every evaluation; sdb_chain_plan then reports lanes_per_chain 0) */
     int32_t refresh_pre;     /* recompute pre_u = log posterior(surrogate(u)) first (surrogate was swapped) */
     int32_t have_G;          /* PREPARE: G_u already holds G(u) (host-evaluated); else the device model fills it */
     sdb_problem problem;
@@ -157,8 +159,10 @@ typedef struct sdb_chain_args {
     /* optional trace: surrogate log posterior of the CURRENT sample as used by step k (the
      * pre_posterior_current_sample the reference writes into its data rows); 0 for MH */
     double *pre_cur;      /* DEVICE [K][C], may be NULL */
-    /* != 0: leave room on every SM for kernels of another stream (the collector's refit running concurrently):
-     * at most one CTA of this kernel per SM (its shared-memory request is padded past half of the SM's) */
+    /* > 0: leave room for kernels of another stream (the collector's refit running concurrently).  Warp-owned launch
+     * shape (RBF surrogate, lanes_per_chain 0): the number of SMs left entirely free -- the launch uses sm_count -
+     * coresident CTAs per wave.  Lane-group shape: at most one CTA of this kernel per SM (its shared-memory request is
+     * padded past half of the SM's). */
     int32_t coresident;
     /* != 0 (additive, RBF surrogate only): the surrogate is evaluated in FP32 -- distances, kernel and the sum over
      * centers on the FP32 pipe, linear tail and the log-posterior in FP64.  The reference evaluates in float64

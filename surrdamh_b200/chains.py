@@ -150,7 +150,7 @@ class ChainBlock:
             refresh_pre=False, lanes=0, stream=None, coresident=False):
         """K fused steps.  The surrogate is evaluated in FP32 when `self.surrogate_f32` is set (RBF surrogates only)."""
         a = self._args(algorithm, L.PHASE_FUSED, surrogate, truth)
-        a.coresident = int(bool(coresident))
+        a.coresident = int(coresident)
         a.n_steps, a.lanes_per_chain, a.refresh_pre = int(n_steps), lanes, int(bool(refresh_pre))
         a.prop_kind, a.prop_scale = proposal.kind, L.ptr(proposal.scale)
         self._fill_rng(a, streams)

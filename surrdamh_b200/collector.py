@@ -253,7 +253,8 @@ class AsyncCollector:
     def __init__(self, collector, device, stream=None, lag=1):
         self.col = collector
         self.device = torch.device(device)
-        self.stream = stream if stream is not None else torch.cuda.Stream(device=self.device)
+        # high priority: the round's critical-path kernels get the next free SM ahead of its own bulk updates
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=self.device, priority=-1)
         self.lag = int(lag)
         self.results = {}
         self.round_events = []                # (start_event, end_event) pairs of the timed rounds

@@ -241,6 +241,8 @@ static chain_fn pick_kernel(int d, int m) {
 // the FP32-surrogate and streamed-surrogate instantiations (sdb_chain_f32.cu, sdb_chain_stream.cu)
 chain_fn sdb_chain_pick_f32(int d, int m);
 chain_fn sdb_chain_pick_stream(int d, int m);
+// warp-owned chains (sdb_chain_wt.cu): mode = SUR_RESIDENT / SUR_F32 / SUR_STREAM
+chain_fn sdb_chain_pick_wt(int d, int m, int mode);
 
 enum { SUR_RESIDENT = 0, SUR_F32 = 1, SUR_STREAM = 2 };
 
@@ -301,7 +303,7 @@ static int validate(const sdb_chain_args *a) {
 }
 
 static int plan(const sdb_chain_args *a, int *L_out, int *threads_out, int *blocks_out, int *smem_out, int *mode_out = nullptr,
-                int *chunk_out = nullptr) {
+                int *chunk_out = nullptr, int *wt_out = nullptr) {
     sdb_device_props dp;
     int rc = sdb_get_device_props(&dp);
     if (rc) return rc;
@@ -341,6 +343,27 @@ static int plan(const sdb_chain_args *a, int *L_out, int *threads_out, int *bloc
     if (a->chain_n > 0) C = a->chain_lo + a->chain_n < C ? a->chain_n : C - a->chain_lo;
     const bool splittable = a->surrogate.kind == SDB_MODEL_RBF;  // only the RBF pair loop is split across lanes
     int L = a->lanes_per_chain;
+    static const bool no_wt = getenv("SDB_NO_WT") != nullptr;
+    if (wt_out) *wt_out = 0;
+    if (L <= 0 && rbf_sur && !no_wt) {
+        // warp-owned chains: 16-warp CTAs, one per SM and wave; the chains are dealt evenly to the warps of the grid (up to
+        // 32 each), so every sub-partition carries the same number of pairs whatever C is.  65 536 chains: 148 CTAs,
+        // 27 or 28 chains per warp, one wave -- against 293 CTAs of 14 warps (3 or 4 per sub-partition) in two waves.
+        // coresident = SMs left entirely free for the kernels of other streams (the collector's refit running beside
+        // the chains): a 16-warp CTA with 128 registers per thread owns its SM, so room is made by launching fewer CTAs.
+        int sms = dp.sm_count - (a->coresident > 0 ? a->coresident : 0);
+        if (sms < 1) sms = 1;
+        const int64_t wave_chains = (int64_t)sms * 16 * 32;
+        const int64_t waves = (C + wave_chains - 1) / wave_chains;
+        int64_t warps_per_sm = (C + sms - 1) / sms;                       // few chains: one warp each, spread over the SMs
+        if (warps_per_sm > 16) warps_per_sm = 16;
+        if (warps_per_sm < 2) warps_per_sm = 2;
+        int64_t blocks = (C + warps_per_sm - 1) / warps_per_sm;
+        if (blocks > sms * waves) blocks = sms * waves;
+        *L_out = 0; *threads_out = (int)warps_per_sm * 32; *blocks_out = (int)blocks; *smem_out = (int)smem;
+        if (wt_out) *wt_out = 1;
+        return SDB_OK;
+    }
     if (L <= 0) {
         L = 1;
         // aim at >= 512 resident threads per SM before giving a chain more lanes
@@ -388,11 +411,13 @@ extern "C" int sdb_chain_run(const sdb_chain_args *args, void *stream) {
     int rc = validate(args);
     if (rc) return rc;
     if (lean_applicable(args)) return lean_launch(args, (cudaStream_t)stream);
-    int L, threads, blocks, smem, mode, chunk;
-    rc = plan(args, &L, &threads, &blocks, &smem, &mode, &chunk);
+    int L, threads, blocks, smem, mode, chunk, wt;
+    rc = plan(args, &L, &threads, &blocks, &smem, &mode, &chunk, &wt);
     if (rc) return rc;
     const int d = args->problem.d, m = args->problem.m;
-    chain_fn fn = mode == SUR_F32 ? sdb_chain_pick_f32(d, m) : mode == SUR_STREAM ? sdb_chain_pick_stream(d, m) : pick_kernel(d, m);
+    chain_fn fn = wt ? sdb_chain_pick_wt(d, m, mode)
+                     : mode == SUR_F32 ? sdb_chain_pick_f32(d, m) : mode == SUR_STREAM ? sdb_chain_pick_stream(d, m) : pick_kernel(d, m);
+    if (wt) L = 1;
     SDB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     sdb_count_launch();
     fn<<<blocks, threads, smem, (cudaStream_t)stream>>>(*args, L, chunk);

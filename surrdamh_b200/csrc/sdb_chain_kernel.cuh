@@ -65,7 +65,9 @@ __device__ __forceinline__ void eval_model_lane(const sdb_smodel &s, int d, int 
 // SM: how the surrogate is held -- 0: tables resident in shared memory, FP64 (poly or RBF); 1: RBF tables resident in
 // FP32, evaluated on the FP32 pipe (surrogate_f32); 2: RBF tables streamed from L2 through a TMA ring of `chunk`-center
 // pieces per evaluation (they do not fit in shared memory).  Separate instantiations, so mode 0 keeps its code.
-template <int D, int M, int SM = 0>
+// WT: warp-owned chains (see sdb_wt_points): launched with L = 1; a warp owns a contiguous run of up to 32 chains, one per
+// lane, and the warps of the grid share the launch's chains evenly (counts differ by at most one).  RBF surrogate only.
+template <int D, int M, int SM = 0, bool WT = false>
 __global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, const int L, const int chunk) {
     constexpr int DD = D ? D : SDB_MAX_D;
     constexpr int UD = D ? D : 1;  // unroll only the specialised sizes
@@ -120,19 +122,31 @@ __global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, c
     sdb_smodel32 sur32;
     sdb_ring ring;
     if constexpr (SM == 1) sur32 = sdb_stage_model32(a.surrogate, d, m, p);
+    // ---- chain ownership ---------------------------------------------------------------------
+    const int64_t c_hi = a.chain_n > 0 ? (a.chain_lo + a.chain_n < C ? a.chain_lo + a.chain_n : C) : C;   // chains [chain_lo, c_hi)
+    int64_t grp;
+    int sub, wt_P = 0, wt_Pmax = 0;
+    if constexpr (WT) {
+        const int wpb = blockDim.x >> 5;
+        const int64_t nW = (int64_t)gridDim.x * wpb, w = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5);
+        const int64_t nC = c_hi - a.chain_lo, q = nC / nW, r = nC % nW;
+        wt_P = (int)(q + (w < r ? 1 : 0));
+        wt_Pmax = (int)(q + (r > 0 ? 1 : 0));
+        grp = (threadIdx.x & 31) < wt_P ? a.chain_lo + w * q + (w < r ? w : r) + (threadIdx.x & 31) : c_hi;
+        sub = 0;
+    } else {
+        const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        grp = a.chain_lo + gtid / L;
+        sub = (int)(gtid % L);
+    }
     if constexpr (SM == 2) {
         const bool is_damh = a.algorithm == SDB_ALG_DAMH;
         const long long evals = !is_damh ? 0
                                 : ((a.phase == SDB_PHASE_PREPARE || a.refresh_pre) ? 1 : 0) +
                                       ((a.phase == SDB_PHASE_FUSED || a.phase == SDB_PHASE_PROPOSE) ? a.n_steps : 0);
-        ring = sdb_ring_init(a.surrogate, d, m, chunk, evals, p);
+        ring = sdb_ring_init(a.surrogate, d, m, chunk, WT ? evals * sdb_wt_passes(wt_Pmax, D, M) : evals, p);
     }
 
-    // ---- chain ownership ---------------------------------------------------------------------
-    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t c_hi = a.chain_n > 0 ? (a.chain_lo + a.chain_n < C ? a.chain_lo + a.chain_n : C) : C;   // chains [chain_lo, c_hi)
-    const int64_t grp = a.chain_lo + gtid / L;
-    const int sub = (int)(gtid % L);
     const bool active = grp < c_hi;
     const int64_t c = active ? grp : (c_hi - 1);  // idle tail lanes shadow the last chain, stores masked
     const bool writer = active && sub == 0;
@@ -143,7 +157,14 @@ __global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, c
                             (int64_t)gridDim.x * blockDim.x <= 148 * 256;
     // the surrogate at a point, called by every lane of the CTA, converged (the proposal of a lockstep step)
     auto eval_sur = [&](const double *X, double *S) {
-        if constexpr (SM == 1) {
+        if constexpr (WT) {
+#pragma unroll UM
+            for (int k = 0; k < MM; ++k)
+                if (k < m) S[k] = 0.0;
+            if constexpr (SM == 1) sdb_rbf32_points_wt<D, M>(sur32, d, m, X, S, wt_P);
+            else if constexpr (SM == 2) sdb_rbf_points_wt_stream<D, M>(ring, d, m, X, S, wt_Pmax);
+            else sdb_rbf_points_wt<D, M>(sur, d, m, X, S, wt_P);
+        } else if constexpr (SM == 1) {
             if (L <= 8 && D <= 4 && M <= 3 && D && M) sdb_rbf32_point_team<D, M, 4>(sur32, d, m, X, S, L);
             else if (L <= 16) sdb_rbf32_point_team<D, M, 2>(sur32, d, m, X, S, L);
             else sdb_rbf32_point_team<D, M, 1>(sur32, d, m, X, S, L);

@@ -717,8 +717,12 @@ static int ns_enqueue(cudaStream_t st, double *S, int64_t ld, int n, int d, int 
     static cudaStream_t aux = nullptr, nxs = nullptr;
     static cudaEvent_t ev_trsm[4], ev_rest[4], ev_next[4];
     if (!aux) {
-        SDB_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
-        SDB_CUDA(cudaStreamCreateWithFlags(&nxs, cudaStreamNonBlocking));
+        // the bulk updates yield to the critical path when SMs are scarce (a refit confined to the few SMs an asynchronous
+        // collector gets beside the chain kernel): lowest priority for `aux`, highest for the next-panel update
+        int prio_lo = 0, prio_hi = 0;
+        SDB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        SDB_CUDA(cudaStreamCreateWithPriority(&aux, cudaStreamNonBlocking, prio_lo));
+        SDB_CUDA(cudaStreamCreateWithPriority(&nxs, cudaStreamNonBlocking, prio_hi));
         for (int i = 0; i < 4; ++i) {
             SDB_CUDA(cudaEventCreateWithFlags(&ev_trsm[i], cudaEventDisableTiming));
             SDB_CUDA(cudaEventCreateWithFlags(&ev_rest[i], cudaEventDisableTiming));

@@ -1,6 +1,8 @@
 // Device functions: forward models (poly / RBF / toy), Gaussian log-posterior.
 // Everything here works on models whose tables already sit in shared memory.
 #pragma once
+#include <type_traits>
+
 #include "sdb_common.cuh"
 
 // A model whose tables have been staged into shared memory.
@@ -618,6 +620,189 @@ __device__ __forceinline__ void sdb_rbf_point_team_stream(sdb_ring &r, int d, in
         for (int k = 0; k < MM; ++k)
             if (k < m) out[k] += sdb_shfl_xor(out[k], off);
     }
+#pragma unroll UM
+    for (int k = 0; k < MM; ++k)
+        if (k < m) {
+            double t = 0.0;
+#pragma unroll UD
+            for (int j = 0; j < DD; ++j)
+                if (j < d) t = fma(x[j], r.tail[j * m + k], t);
+            out[k] += r.tail[d * m + k] + t;
+        }
+}
+
+// ---------------------------------------------------------------------------------------
+// Warp-owned chains (chain_kernel<..., WT = true>): a warp owns P <= 32 chains, lane p < P holds chain p.  For the
+// surrogate of a lockstep step ALL 32 lanes split the centers (lane t takes centers t, t + 32, ...) and evaluate the
+// warp's points in groups of NP = 8 (the tail of the warp's points in a group of 4 / 2 / 1): a center / weight load
+// serves NP pairs, and -- the reason for this layout -- P is ANY integer, so C chains spread over exactly the warps
+// the GPU holds in one wave (65 536 chains = 2368 warps x 27.67) instead of power-of-two lane groups that leave a
+// sub-partition with 3 warps next to one with 4.  The 32 partial sums of a point are combined by a fixed tree
+// (xor 16, 8, 4, 2, 1), whatever P and NP are: the result does not depend on how the chains are sharded.
+// ---------------------------------------------------------------------------------------
+// largest group: the group's points and sums live in registers (NP (d + m) doubles) beside the chain state
+__host__ __device__ constexpr int sdb_wt_group_max(int D, int M) {
+    return (D == 0 || M == 0) ? 2 : (D + M <= 3) ? 8 : (D + M <= 7) ? 4 : 2;
+}
+// v[NP]: this lane's partial sums of NP points.  Returns, on every lane, the 32-lane total of point
+// (lane * NP) >> 5: halving exchanges while more than one point is held, plain butterflies after.
+template <int NP>
+__device__ __forceinline__ double sdb_wt_reduce(const double *v, int lane) {
+    double r[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) r[i] = v[i];
+    int off = 16;
+#pragma unroll
+    for (int h = NP / 2; h >= 1; h >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const double keep = up ? r[h + i] : r[i];
+            const double send = up ? r[i] : r[h + i];
+            r[i] = keep + sdb_shfl_xor(send, off);
+        }
+        off >>= 1;
+    }
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        if (off >= 1) r[0] += sdb_shfl_xor(r[0], off);
+        off >>= 1;
+    }
+    return r[0];
+}
+
+// One group: points of lanes g0 .. g0 + NP - 1.  partial(xs, acc) runs this lane's share of the pair loop.
+template <int D, int M, int NP, class F>
+__device__ __forceinline__ void sdb_wt_group(F &partial, int d, int m, const double *x, double *out, int g0, int lane) {
+    constexpr int DD = D ? D : SDB_MAX_D;
+    constexpr int UD = D ? D : 1;
+    constexpr int MM = M ? M : SDB_MAX_M;
+    constexpr int UM = M ? M : 1;
+    double xs[NP][DD], acc[NP][MM];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+#pragma unroll UD
+        for (int j = 0; j < DD; ++j)
+            if (j < d) xs[p][j] = sdb_shfl(x[j], g0 + p);
+#pragma unroll UM
+        for (int k = 0; k < MM; ++k)
+            if (k < m) acc[p][k] = 0.0;
+    }
+    partial(xs, acc, std::integral_constant<int, NP>());
+    const int src = ((lane - g0) & (NP - 1)) * (32 / NP);
+    const bool mine = lane >= g0 && lane < g0 + NP;
+#pragma unroll UM
+    for (int k = 0; k < MM; ++k)
+        if (k < m) {
+            double v[NP];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) v[p] = acc[p][k];
+            const double t = sdb_shfl(sdb_wt_reduce<NP>(v, lane), src);
+            if (mine) out[k] = t;
+        }
+}
+
+// All groups of a warp's P points (P warp-uniform).  Full warp, converged.  out[] of lanes >= P is left untouched.
+template <int D, int M, class F>
+__device__ __forceinline__ void sdb_wt_points(F &partial, int d, int m, const double *x, double *out, int P) {
+    const int lane = threadIdx.x & 31;
+    constexpr int GN = sdb_wt_group_max(D, M);
+    int g0 = 0;
+    while (g0 < P) {
+        const int rem = P - g0;
+        // a pass costs about its group size: 7 points ride in a group of 8 and 3 in a group of 4, but 5 = 4 + 1 and 6 = 4 + 2
+        if (GN >= 8 && rem >= 7) { sdb_wt_group<D, M, GN >= 8 ? 8 : 1>(partial, d, m, x, out, g0, lane); g0 += 8; }
+        else if (GN >= 4 && rem >= 3) { sdb_wt_group<D, M, GN >= 4 ? 4 : 1>(partial, d, m, x, out, g0, lane); g0 += 4; }
+        else if (rem >= 2) { sdb_wt_group<D, M, 2>(partial, d, m, x, out, g0, lane); g0 += 2; }
+        else { sdb_wt_group<D, M, 1>(partial, d, m, x, out, g0, lane); g0 += 1; }
+    }
+}
+// number of sdb_wt_group passes sdb_wt_points makes for P points
+__host__ __device__ inline int sdb_wt_passes(int P, int D, int M) {
+    const int GN = sdb_wt_group_max(D, M);
+    int n = 0, g0 = 0;
+    while (g0 < P) { const int rem = P - g0; g0 += (GN >= 8 && rem >= 7) ? 8 : (GN >= 4 && rem >= 3) ? 4 : rem >= 2 ? 2 : 1; ++n; }
+    return n;
+}
+
+// resident FP64 tables
+template <int D, int M>
+__device__ __forceinline__ void sdb_rbf_points_wt(const sdb_smodel &s, int d, int m, const double *x, double *out, int P) {
+    const int lane = threadIdx.x & 31;
+    auto partial = [&](auto &xs, auto &acc, auto np) {
+        sdb_rbf_partialn_st<D, M, 32, decltype(np)::value>(s, d, m, xs, acc, lane, 32);
+    };
+    sdb_wt_points<D, M>(partial, d, m, x, out, P);
+    sdb_rbf_add_tail<D, M>(s, d, m, x, out);
+}
+
+// FP32 tables (see above): the per-lane sums are FP32, the tree and the tail FP64
+template <int D, int M>
+__device__ __forceinline__ void sdb_rbf32_points_wt(const sdb_smodel32 &s, int d, int m, const double *x, double *out, int P) {
+    constexpr int DD = D ? D : SDB_MAX_D;
+    constexpr int UD = D ? D : 1;
+    constexpr int MM = M ? M : SDB_MAX_M;
+    constexpr int UM = M ? M : 1;
+    const int lane = threadIdx.x & 31;
+    auto partial = [&](auto &xs, auto &acc, auto np) {
+        constexpr int NP = decltype(np)::value;
+        float xf[NP][DD], af[NP][MM];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+#pragma unroll UD
+            for (int j = 0; j < DD; ++j)
+                if (j < d) xf[p][j] = (float)(xs[p][j] - s.shift[j]);
+#pragma unroll UM
+            for (int k = 0; k < MM; ++k)
+                if (k < m) af[p][k] = 0.0f;
+        }
+        sdb_rbf32_partialn_st<D, M, 32, NP>(s, d, m, xf, af, lane, 32);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+#pragma unroll UM
+            for (int k = 0; k < MM; ++k)
+                if (k < m) acc[p][k] = (double)af[p][k];
+        }
+    };
+    sdb_wt_points<D, M>(partial, d, m, x, out, P);
+#pragma unroll UM
+    for (int k = 0; k < MM; ++k)
+        if (k < m) {
+            double t = 0.0;
+#pragma unroll UD
+            for (int j = 0; j < DD; ++j)
+                if (j < d) t = fma(x[j], s.tail[j * m + k], t);
+            out[k] += s.tail[d * m + k] + t;
+        }
+}
+
+// streamed tables: every group pass walks the ring once.  Full CTA, converged (barriers inside), so P is the CTA-uniform
+// maximum over the launch's warps (lanes beyond a warp's own count carry a shadow point whose result is unused).
+template <int D, int M>
+__device__ __forceinline__ void sdb_rbf_points_wt_stream(sdb_ring &r, int d, int m, const double *x, double *out, int P) {
+    constexpr int UD = D ? D : 1;
+    constexpr int UM = M ? M : 1;
+    constexpr int DD = D ? D : SDB_MAX_D;
+    constexpr int MM = M ? M : SDB_MAX_M;
+    const int lane = threadIdx.x & 31;
+    auto partial = [&](auto &xs, auto &acc, auto np) {
+        for (int ci = 0; ci < r.nchunks; ++ci) {
+            const int st = (int)(r.consumed & 1);
+            sdb_mbar_wait(&r.full[st], (r.phase_bits >> st) & 1);
+            r.phase_bits ^= 1 << st;
+            const long long c0 = (long long)ci * r.chunk;
+            sdb_smodel s;
+            s.kind = SDB_MODEL_RBF; s.kernel_type = r.kernel_type;
+            s.n_centers = (int)((r.n - c0) < r.chunk ? (r.n - c0) : r.chunk);
+            s.centers = (const double *)(r.base + (size_t)st * (r.cbytes + r.wbytes));
+            s.coefs = (const double *)(r.base + (size_t)st * (r.cbytes + r.wbytes) + r.cbytes);
+            sdb_rbf_partialn_st<D, M, 32, decltype(np)::value>(s, d, m, xs, acc, lane, 32);
+            ++r.consumed;
+            __syncthreads();      // every warp is done with stage st
+            if (r.issued < r.total) sdb_ring_issue(r, d, m);
+        }
+    };
+    sdb_wt_points<D, M>(partial, d, m, x, out, P);
 #pragma unroll UM
     for (int k = 0; k < MM; ++k)
         if (k < m) {

@@ -166,7 +166,8 @@ class LockstepSampler:
                     surrogate, swapped = new, True
             strm = None if self.streams is None else self.streams(i, done, K)
             if self.truth is not None:
-                blk.run(kind, K, prop, surrogate, self.truth, trace=trace, streams=strm, refresh_pre=swapped)
+                blk.run(kind, K, prop, surrogate, self.truth, trace=trace, streams=strm, refresh_pre=swapped,
+                        coresident=self.conf.reserve_sms if acol is not None else 0)
             else:
                 self._run_split(kind, K, prop, surrogate, trace, strm, swapped, collects)
             swapped = False
