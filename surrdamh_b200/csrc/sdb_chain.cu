@@ -353,15 +353,17 @@ static int plan(const sdb_chain_args *a, int *L_out, int *threads_out, int *bloc
         // the chains): a 16-warp CTA with 128 registers per thread owns its SM, so room is made by launching fewer CTAs.
         int sms = dp.sm_count - (a->coresident > 0 ? a->coresident : 0);
         if (sms < 1) sms = 1;
+        // More than 32 chains per warp: the grid stays at one CTA per SM and every warp works through several runs of
+        // chains ("waves") inside the kernel, so the SMs left free are never taken by a second wave of CTAs.
         const int64_t wave_chains = (int64_t)sms * 16 * 32;
         const int64_t waves = (C + wave_chains - 1) / wave_chains;
         int64_t warps_per_sm = (C + sms - 1) / sms;                       // few chains: one warp each, spread over the SMs
         if (warps_per_sm > 16) warps_per_sm = 16;
         if (warps_per_sm < 2) warps_per_sm = 2;
         int64_t blocks = (C + warps_per_sm - 1) / warps_per_sm;
-        if (blocks > sms * waves) blocks = sms * waves;
+        if (blocks > sms) blocks = sms;
         *L_out = 0; *threads_out = (int)warps_per_sm * 32; *blocks_out = (int)blocks; *smem_out = (int)smem;
-        if (wt_out) *wt_out = 1;
+        if (wt_out) *wt_out = (int)waves;
         return SDB_OK;
     }
     if (L <= 0) {
@@ -417,7 +419,7 @@ extern "C" int sdb_chain_run(const sdb_chain_args *args, void *stream) {
     const int d = args->problem.d, m = args->problem.m;
     chain_fn fn = wt ? sdb_chain_pick_wt(d, m, mode)
                      : mode == SUR_F32 ? sdb_chain_pick_f32(d, m) : mode == SUR_STREAM ? sdb_chain_pick_stream(d, m) : pick_kernel(d, m);
-    if (wt) L = 1;
+    if (wt) L = wt;     // warp-owned chains: the kernel's second argument is the number of waves
     SDB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     sdb_count_launch();
     fn<<<blocks, threads, smem, (cudaStream_t)stream>>>(*args, L, chunk);

@@ -68,7 +68,7 @@ __device__ __forceinline__ void eval_model_lane(const sdb_smodel &s, int d, int 
 // WT: warp-owned chains (see sdb_wt_points): launched with L = 1; a warp owns a contiguous run of up to 32 chains, one per
 // lane, and the warps of the grid share the launch's chains evenly (counts differ by at most one).  RBF surrogate only.
 template <int D, int M, int SM = 0, bool WT = false>
-__global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, const int L, const int chunk) {
+__global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, const int L_or_waves, const int chunk) {
     constexpr int DD = D ? D : SDB_MAX_D;
     constexpr int UD = D ? D : 1;  // unroll only the specialised sizes
     constexpr int MM = M ? M : SDB_MAX_M;
@@ -123,30 +123,35 @@ __global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, c
     sdb_ring ring;
     if constexpr (SM == 1) sur32 = sdb_stage_model32(a.surrogate, d, m, p);
     // ---- chain ownership ---------------------------------------------------------------------
+    // WT: the kernel's second argument is the number of WAVES -- every warp works through `waves` runs of chains one after
+    // the other (a persistent grid of at most one CTA per SM, so SMs the launch leaves free stay free until it ends)
+    const int waves = WT ? L_or_waves : 1;
+    const int L = WT ? 1 : L_or_waves;
     const int64_t c_hi = a.chain_n > 0 ? (a.chain_lo + a.chain_n < C ? a.chain_lo + a.chain_n : C) : C;   // chains [chain_lo, c_hi)
+    const int64_t wt_nW = (int64_t)gridDim.x * (blockDim.x >> 5) * waves;      // virtual warps
+    const int64_t wt_q = (c_hi - a.chain_lo) / wt_nW, wt_r = (c_hi - a.chain_lo) % wt_nW;
+    const int wt_Pmax = (int)(wt_q + (wt_r > 0 ? 1 : 0));
+    if constexpr (SM == 2) {
+        const bool is_damh = a.algorithm == SDB_ALG_DAMH;
+        const long long evals = !is_damh ? 0
+                                : ((a.phase == SDB_PHASE_PREPARE || a.refresh_pre) ? 1 : 0) +
+                                      ((a.phase == SDB_PHASE_FUSED || a.phase == SDB_PHASE_PROPOSE) ? a.n_steps : 0);
+        ring = sdb_ring_init(a.surrogate, d, m, chunk, WT ? evals * sdb_wt_passes(wt_Pmax, D, M) * waves : evals, p);
+    }
+
+    for (int wave = 0; wave < waves; ++wave) {
     int64_t grp;
-    int sub, wt_P = 0, wt_Pmax = 0;
+    int sub, wt_P = 0;
     if constexpr (WT) {
-        const int wpb = blockDim.x >> 5;
-        const int64_t nW = (int64_t)gridDim.x * wpb, w = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5);
-        const int64_t nC = c_hi - a.chain_lo, q = nC / nW, r = nC % nW;
-        wt_P = (int)(q + (w < r ? 1 : 0));
-        wt_Pmax = (int)(q + (r > 0 ? 1 : 0));
-        grp = (threadIdx.x & 31) < wt_P ? a.chain_lo + w * q + (w < r ? w : r) + (threadIdx.x & 31) : c_hi;
+        const int64_t w = (int64_t)wave * (wt_nW / waves) + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        wt_P = (int)(wt_q + (w < wt_r ? 1 : 0));
+        grp = (threadIdx.x & 31) < wt_P ? a.chain_lo + w * wt_q + (w < wt_r ? w : wt_r) + (threadIdx.x & 31) : c_hi;
         sub = 0;
     } else {
         const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         grp = a.chain_lo + gtid / L;
         sub = (int)(gtid % L);
     }
-    if constexpr (SM == 2) {
-        const bool is_damh = a.algorithm == SDB_ALG_DAMH;
-        const long long evals = !is_damh ? 0
-                                : ((a.phase == SDB_PHASE_PREPARE || a.refresh_pre) ? 1 : 0) +
-                                      ((a.phase == SDB_PHASE_FUSED || a.phase == SDB_PHASE_PROPOSE) ? a.n_steps : 0);
-        ring = sdb_ring_init(a.surrogate, d, m, chunk, WT ? evals * sdb_wt_passes(wt_Pmax, D, M) : evals, p);
-    }
-
     const bool active = grp < c_hi;
     const int64_t c = active ? grp : (c_hi - 1);  // idle tail lanes shadow the last chain, stores masked
     const bool writer = active && sub == 0;
@@ -409,5 +414,6 @@ __global__ void __launch_bounds__(512, 1) chain_kernel(const sdb_chain_args a, c
             for (int i = 0; i < NMOM; ++i) a.state.moments[(size_t)i * C + c] = mom[i];
         }
     }
+    }   // waves
 }
 

@@ -710,9 +710,9 @@ __device__ __forceinline__ void sdb_wt_points(F &partial, int d, int m, const do
     int g0 = 0;
     while (g0 < P) {
         const int rem = P - g0;
-        // a pass costs about its group size: 7 points ride in a group of 8 and 3 in a group of 4, but 5 = 4 + 1 and 6 = 4 + 2
-        if (GN >= 8 && rem >= 7) { sdb_wt_group<D, M, GN >= 8 ? 8 : 1>(partial, d, m, x, out, g0, lane); g0 += 8; }
-        else if (GN >= 4 && rem >= 3) { sdb_wt_group<D, M, GN >= 4 ? 4 : 1>(partial, d, m, x, out, g0, lane); g0 += 4; }
+        // a pass costs about its group size (the small groups a little more per point), so the binary decomposition of P
+        if (GN >= 8 && rem >= 8) { sdb_wt_group<D, M, GN >= 8 ? 8 : 1>(partial, d, m, x, out, g0, lane); g0 += 8; }
+        else if (GN >= 4 && rem >= 4) { sdb_wt_group<D, M, GN >= 4 ? 4 : 1>(partial, d, m, x, out, g0, lane); g0 += 4; }
         else if (rem >= 2) { sdb_wt_group<D, M, 2>(partial, d, m, x, out, g0, lane); g0 += 2; }
         else { sdb_wt_group<D, M, 1>(partial, d, m, x, out, g0, lane); g0 += 1; }
     }
@@ -721,7 +721,7 @@ __device__ __forceinline__ void sdb_wt_points(F &partial, int d, int m, const do
 __host__ __device__ inline int sdb_wt_passes(int P, int D, int M) {
     const int GN = sdb_wt_group_max(D, M);
     int n = 0, g0 = 0;
-    while (g0 < P) { const int rem = P - g0; g0 += (GN >= 8 && rem >= 7) ? 8 : (GN >= 4 && rem >= 3) ? 4 : rem >= 2 ? 2 : 1; ++n; }
+    while (g0 < P) { const int rem = P - g0; g0 += (GN >= 8 && rem >= 8) ? 8 : (GN >= 4 && rem >= 4) ? 4 : rem >= 2 ? 2 : 1; ++n; }
     return n;
 }
 
