@@ -354,7 +354,7 @@ class Run:
         import torch
 
         from surrdamh_b200.chains import ChainBlock, Proposal, Trace
-        from surrdamh_b200.collector import AsyncCollector, Collector
+        from surrdamh_b200.collector import AsyncCollector, Collector, PipelinedCollector
         from surrdamh_b200.device import DeviceProblem
         self.torch = torch
         self.w, self.C, self.rank, self.world, self.dev = w, C_, rank, world, dev
@@ -367,13 +367,15 @@ class Run:
         self.precision = precision
         self.prop = Proposal(d, w["proposal_std"], device=dev)
         self.col = self.acol = None
-        self.lag = lag if collector == "async" else 0
-        self.reserve_sms = reserve_sms if collector == "async" else 0
+        self.lag = lag if collector != "sync" else 0
+        self.reserve_sms = reserve_sms if collector != "sync" else 0
         if w["updated"]:
             self.col = Collector(self.updater, "rbf", d, m, kernel_type=w["kernel_type"], rank=rank, world=world,
                                  snapshots_per_refit=w["snapshots_per_refit"], refit_mode=refit_mode, device=dev)
             self.col.model = self.sur
             if collector == "async":
+                self.acol = PipelinedCollector(self.col, dev, lag=lag)
+            elif collector == "async-serial":
                 self.acol = AsyncCollector(self.col, dev, lag=lag)
             self.traces = [Trace(K, C_, d, m, dev, snapshots=True, full=False) for _ in range(self.lag + 1)]
         else:
@@ -494,6 +496,13 @@ class Run:
         launches = int(L.lib().sdb_launch_count(1))
         kern = [(a.elapsed_time(b), sw) for a, b, sw in self.kern_ev]
         rounds = [a.elapsed_time(b) for a, b in (self.acol.round_events if self.acol is not None else self.round_ev)]
+        stages = None
+        if getattr(self.acol, "stage_events", None):
+            ev = self.acol.stage_events
+            solved = [t.elapsed_time(s_) for _, t, s_, _ in ev if s_ is not None]
+            stages = {"thin": float(np.mean([a.elapsed_time(t) for a, t, _, _ in ev])),
+                      "solve_on_duty_rank": float(np.mean(solved)) if solved else None, "solves_here": len(solved)}
+            ev.clear()
         self.kern_ev.clear(); self.round_ev.clear()
         if self.acol is not None:
             self.acol.round_events.clear()
@@ -503,13 +512,15 @@ class Run:
         self.kern_ev.clear(); self.round_ev.clear()
         if self.acol is not None:
             self.acol.round_events.clear()
+            if getattr(self.acol, "stage_events", None):
+                self.acol.stage_events.clear()
         failures = 0
         if self.col is not None:
             self.col.poll_status(wait=True)
             failures = sum(1 for s in self.col.status_log if s[1])
         total = float(self.C) * self.K * steps * self.world
         return dict(value=total / (ms_total * 1e-3), ms_per_step=ms_total / steps, steps=steps, launches=launches, kern=kern,
-                    rounds=rounds, wall=(wall0, wall1), refit_failures=failures,
+                    rounds=rounds, stages=stages, wall=(wall0, wall1), refit_failures=failures,
                     e2e=dict(value=float(self.C) * self.K * e2e_steps * self.world / (ms_e2e * 1e-3), unit="chain steps/s",
                              h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_steps, ms_per_step=ms_e2e / e2e_steps,
                              returns="per block and chain: final sample, counters, running first / second moments of the chain, "
@@ -658,7 +669,7 @@ def run_ours(args):
     if args.solver and w["surrogate"] == "rbf":
         w["solver_type"] = args.solver
     collector = args.collector or "async"
-    refit_mode = args.refit_mode or "broadcast"
+    refit_mode = args.refit_mode or ("rotate" if world > 1 else "broadcast")
 
     # ---- CPU baseline (rank 0, N == 1 only), before the timed GPU region -------------------------------
     cpu = None
@@ -693,12 +704,14 @@ def run_ours(args):
     # ---- strong scaling: the same 65536 chains split evenly over the ranks ------------------------------------
     strong = None
     if world > 1 and w["updated"] and not args.no_extras and w["chains"] % world == 0:
-        srun = Run(w, w["chains"] // world, rank, world, dev, collector, refit_mode, args.lag, reserve_sms=args.reserve_sms)
+        slag = args.strong_lag or world
+        srun = Run(w, w["chains"] // world, rank, world, dev, collector, refit_mode, slag, reserve_sms=args.reserve_sms)
         srec = srun.measure(args.steps, args.warmup, e2e_steps)
         strong = {"scaling": "strong", "chains_total": w["chains"], "chains_per_gpu": w["chains"] // world, "value": srec["value"],
                   "unit": "chain steps/s", "ms_per_step": srec["ms_per_step"], "e2e": srec["e2e"],
                   "kernel_ms": float(np.mean([k for k, _ in srec["kern"]])),
-                  "round_ms": float(np.mean(srec["rounds"])) if srec["rounds"] else None, "gpu_launches": srec["launches"]}
+                  "round_ms": float(np.mean(srec["rounds"])) if srec["rounds"] else None, "gpu_launches": srec["launches"],
+                  "lag_blocks": srun.lag, "stages_ms": srec.get("stages")}
         del srun
 
     # ---- the FP32-surrogate variant of the same workload (second line; the headline stays FP64) ---------------------------
@@ -760,12 +773,16 @@ def run_ours(args):
         n_c = w["centers"]
         round_ms = float(np.mean(rec["rounds"]))
         flop = n_c ** 3 / 3.0
-        out["collector"] = {"mode": collector, "refit_mode": refit_mode, "lag_blocks": run.lag, "reserved_sms": run.reserve_sms, "round_ms": round_ms,
+        out["collector"] = {"mode": collector, "refit_mode": refit_mode, "lag_blocks": run.lag, "reserved_sms": run.reserve_sms, "round_ms": round_ms, "stages_ms": rec.get("stages"),
                             "rounds": len(rec["rounds"]), "refit_failures": rec["refit_failures"], "solver": w.get("solver_type"),
                             "system_size": n_c + d + 1,
                             "what": "select + all-gather + masked thinning + system build + dense solve + broadcast; "
-                                    + ("enqueued on a side stream, surrogate of round b used from block b+%d" % (run.lag + 1)
-                                       if collector == "async" else "between blocks on the sampling stream")}
+                                    + ("between blocks on the sampling stream" if collector == "sync" else
+                                       ("two pipelined stages on side streams (thin: every rank; solve: the rank on duty), "
+                                        if collector == "async" else "one serial round on a side stream, ")
+                                       + "surrogate of round b used from block b+%d; round_ms = latency from the end of "
+                                         "the block to the assembled model, on the %d SMs the chain kernel leaves free"
+                                       % (run.lag + 1, run.reserve_sms))}
         out["roofline_refit"] = {"bound": "fp64-tensor (DMMA)", "achieved": flop / (round_ms * 1e-3) / 1e12, "peak": peak_tf,
                                  "unit": "TFLOP/s", "frac": flop / (round_ms * 1e-3) / 1e12 / peak_tf, "flops_per_round": flop,
                                  "round_ms": round_ms,
@@ -838,11 +855,12 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling record (N > 1) and the cfg2 / cfg5 records (N = 1)")
-    ap.add_argument("--collector", default="", choices=["", "sync", "async"],
+    ap.add_argument("--collector", default="", choices=["", "sync", "async", "async-serial"],
                     help="async (default): the collector round runs on a side stream beside the next block and its surrogate is "
                          "used from block b+2 on, like the reference's separate collector process; sync: between blocks")
     ap.add_argument("--refit-mode", default="", choices=["", "broadcast", "rotate", "replicated"])
-    ap.add_argument("--lag", type=int, default=1, help="blocks of lag of the asynchronous collector")
+    ap.add_argument("--lag", type=int, default=1, help="blocks of lag of the asynchronous collector (weak-scaling record)")
+    ap.add_argument("--strong-lag", type=int, default=0, help="the same for the strong-scaling record (0: the number of GPUs)")
     ap.add_argument("--reserve-sms", type=int, default=16, help="SMs the chain kernel leaves to the asynchronous collector's kernels")
     ap.add_argument("--profile", type=int, default=0, help="run this many bench steps inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()

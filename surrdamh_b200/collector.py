@@ -183,8 +183,13 @@ class Collector:
             dist.broadcast(out, src=duty, group=self.group)
         self.model = up.adopt_pack(out)
         self.no_snapshots = int(up.no_keep)
-        # the round's status row goes to pinned memory asynchronously and is looked at one round later
-        status = up.pack_views(out)[3]
+        self._queue_status(up.pack_views(out)[3])
+        self.no_refits += 1
+        self.history.append((global_step, None))
+        return True
+
+    def _queue_status(self, status):
+        """The round's status row goes to pinned memory asynchronously (current stream) and is looked at one round later."""
         if status.is_cuda:
             pinned = torch.empty((16,), dtype=torch.float64).pin_memory()
             pinned.copy_(status, non_blocking=True)
@@ -194,9 +199,6 @@ class Collector:
         else:
             self._status_pending.append((None, status.clone(), self.no_refits))
         self.poll_status()
-        self.no_refits += 1
-        self.history.append((global_step, None))
-        return True
 
     def poll_status(self, wait=False):
         """Move finished rounds' status rows to `status_log` [(round, failed, solver info, rows kept, new snapshots)]."""
@@ -237,6 +239,36 @@ class Collector:
         self.fixed = False
 
 
+class _Lane:
+    """A CUDA stream of its own -- or, on the CPU (the gloo tests drive the same code), nothing at all."""
+
+    def __init__(self, device, priority=0, stream=None):
+        self.cuda = torch.device(device).type == "cuda"
+        self.stream = (stream if stream is not None else torch.cuda.Stream(device=device, priority=priority)) if self.cuda else None
+
+    def __enter__(self):
+        if self.cuda:
+            self._ctx = torch.cuda.stream(self.stream)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.cuda:
+            self._ctx.__exit__(*exc)
+        return False
+
+    def wait(self, event):
+        if self.cuda and event is not None:
+            self.stream.wait_event(event)
+
+    def record(self, timing=False):
+        if not self.cuda:
+            return None
+        ev = torch.cuda.Event(enable_timing=timing)
+        ev.record(self.stream)
+        return ev
+
+
 class AsyncCollector:
     """The collector as a concurrent actor, like the reference's separate COLLECTOR process
     (process_COLLECTOR.py runs beside the samplers, which keep stepping with the surrogate they have until a
@@ -254,21 +286,18 @@ class AsyncCollector:
         self.col = collector
         self.device = torch.device(device)
         # high priority: the round's critical-path kernels get the next free SM ahead of its own bulk updates
-        self.stream = stream if stream is not None else torch.cuda.Stream(device=self.device, priority=-1)
+        self.lane = _Lane(self.device, priority=-1, stream=stream)
+        self.stream = self.lane.stream
         self.lag = int(lag)
         self.results = {}
         self.round_events = []                # (start_event, end_event) pairs of the timed rounds
 
     def submit(self, b, trace, K, chain_done_event, step, timed=False):
-        with torch.cuda.stream(self.stream):
-            self.stream.wait_event(chain_done_event)
-            r0 = r1 = None
-            if timed:
-                r0 = torch.cuda.Event(enable_timing=True)
-                r0.record()
+        with self.lane:
+            self.lane.wait(chain_done_event)
+            r0 = self.lane.record(timing=True) if timed else None
             did = self.col.round(trace, K, step)
-            r1 = torch.cuda.Event(enable_timing=timed)
-            r1.record()
+            r1 = self.lane.record(timing=timed)
             if timed:
                 self.round_events.append((r0, r1))
         self.results[b] = (r1, self.col.model if did else None)
@@ -282,3 +311,118 @@ class AsyncCollector:
 
     def close(self):
         self.results.clear()
+
+
+class PipelinedCollector(AsyncCollector):
+    """The asynchronous collector with a round split into its two stages, each on a stream of its own:
+
+      thin   select + ONE all-gather + candidates + greedy thinning + compaction.  Strictly sequential from round to round
+             (round b+1 thins the centers round b kept) but cheap -- one SM for about a millisecond -- so EVERY rank runs
+             it: the center sets stay identical on all ranks without being sent.
+      solve  the dense solve of the thinned set.  It depends on the thin stage of ITS round only, so round b+1 is thinned
+             while round b is still being solved, and with `refit_mode: "rotate"` the solves of consecutive rounds run on
+             different ranks at the same time: rank b mod N solves round b and broadcasts [COEFS | status] (ONE
+             broadcast, on a communicator of its own so that it never queues behind an all-gather).
+
+    A third stream receives the broadcast and assembles the model of the round, [COEFS | centers | observations | status]
+    -- or a copy of the previous round's model when the solve failed.  The sampling stream switches to the surrogate
+    of round b at the start of block b + lag + 1, as with AsyncCollector; with N ranks the solve of a round may take N
+    block periods, which is what makes a STRONG-scaling run (few chains per GPU, short blocks) keep its refit rate: the
+    reference's collector is likewise a separate process the samplers never wait for (process_COLLECTOR.py:57-113).
+
+    Rounds before the collector reaches its fixed shapes (center set still growing) run serially like AsyncCollector's.
+    """
+
+    def __init__(self, collector, device, lag=1, make_group=True):
+        super().__init__(collector, device, lag=lag)
+        col = collector
+        self.thin = self.lane                           # the thin stage runs where AsyncCollector's serial rounds run
+        self.solve = _Lane(device, priority=0)
+        self.asm = _Lane(device, priority=-1)
+        self.cuda = self.thin.cuda
+        self.bgroup = col.group
+        if col.world > 1 and col.refit_mode != "replicated" and make_group:
+            if getattr(col, "_bgroup", None) is None:
+                import torch.distributed as dist
+                col._bgroup = dist.new_group()          # collective: every rank constructs its PipelinedCollector
+            self.bgroup = col._bgroup
+        self.nring = self.lag + 4
+        self.slots = None
+        self.n_piped = 0
+        self.stage_events = []                          # timed rounds: (start, thinned, solved | None, assembled)
+        self.last = None                                # slot of the newest round
+
+    # ---- state ---------------------------------------------------------------------------------------------------
+    def _start(self):
+        """Enter the pipeline from the collector's current packed state (identical on every rank)."""
+        col, up = self.col, self.col.updater
+        cur = col.ring[col.gen % len(col.ring)]
+        self.slots = []
+        for _ in range(self.nring):
+            X, Y, meta = up.new_thin_state()
+            self.slots.append(dict(X=X, Y=Y, meta=meta, result=up.new_result(), pack=up.new_pack()))
+        s0 = self.slots[-1]                              # "round -1": the state the first pipelined round starts from
+        _, X0, Y0, _ = up.pack_views(cur)
+        s0["X"].copy_(X0)
+        s0["Y"].copy_(Y0)
+        s0["pack"].copy_(cur)
+        self.last = self.nring - 1
+
+    def submit(self, b, trace, K, chain_done_event, step, timed=False):
+        col, up = self.col, self.col.updater
+        if not col.fixed:
+            if not (col.model is not None and col._can_go_fixed()):
+                return super().submit(b, trace, K, chain_done_event, step, timed)     # general-path round, serial
+            with self.thin:
+                col._enter_fixed()
+        with self.thin:
+            self.thin.wait(chain_done_event)
+            if self.slots is None:
+                self._start()
+            prev, cur = self.slots[self.last], self.slots[(self.last + 1) % self.nring]
+            t0 = self.thin.record(timing=True) if timed else None
+            block = col.select(trace, K)
+            gathered = col.gather(block)
+            up.thin_stage(prev["X"], prev["Y"], gathered.reshape(-1), col.world, col.quota, cur["X"], cur["Y"], cur["meta"])
+            ev_t = self.thin.record(timing=timed)
+        duty = col.duty_rank(col.no_refits)
+        everyone = col.world == 1 or col.refit_mode == "replicated"
+        ev_s = None
+        if everyone or col.rank == duty:
+            with self.solve:
+                self.solve.wait(ev_t)
+                up.solve_stage(cur["X"], cur["Y"], cur["meta"], cur["result"])
+                ev_s = self.solve.record(timing=timed)
+        with self.asm:
+            self.asm.wait(ev_t)
+            self.asm.wait(ev_s)
+            if not everyone:
+                import torch.distributed as dist
+                dist.broadcast(cur["result"], src=duty, group=self.bgroup)
+            up.assemble(cur["result"], cur["X"], cur["Y"], prev["pack"], cur["pack"])
+            col._queue_status(up.pack_views(cur["pack"])[3])
+            ev_m = self.asm.record(timing=timed)
+        if timed:
+            self.stage_events.append((t0, ev_t, ev_s, ev_m))
+            self.round_events.append((t0, ev_m))
+        self.last = (self.last + 1) % self.nring
+        self.n_piped += 1
+        col.no_refits += 1
+        col.history.append((step, None))
+        self.results[b] = (ev_m, up.model_of_pack(cur["pack"]))
+
+    def close(self):
+        """End of a stage: the collector and its updater take over the newest round's state (call after the sampling
+        stream has waited for every round)."""
+        if self.slots is not None:
+            col, up = self.col, self.col.updater
+            cur = self.slots[self.last]
+            if self.cuda:
+                torch.cuda.current_stream().wait_stream(self.asm.stream)
+            nxt = col.ring[(col.gen + 1) % len(col.ring)]
+            nxt.copy_(cur["pack"])
+            col.gen += 1
+            col.model = up.adopt_pack(nxt)
+            col.no_snapshots = int(up.no_keep)
+            self.slots = None
+        super().close()

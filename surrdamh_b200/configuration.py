@@ -19,6 +19,8 @@ ADDITIVE keys of this implementation (ignored by the reference, never renames):
   collector_async      true: the refit of block b runs on a side stream while the next blocks step; its
                        surrogate is used from block b + refit_lag + 1 on (default false: used from block b + 1)
   refit_lag            blocks of lag of the asynchronous collector (default 1)
+  collector_pipelined  (with collector_async, default true) the round runs as two pipelined stages -- thinning on every
+                       rank, the dense solve on the rank on duty -- so consecutive rounds overlap (PipelinedCollector)
   reserve_sms          SMs the chain kernel leaves free for the asynchronous collector's kernels (default 16; the
                        chain CTAs own their SMs, so the refit needs SMs of its own to run beside them)
   surrogate_precision  'f64' (default, the reference's arithmetic) | 'f32': an RBF surrogate is evaluated on the FP32
@@ -106,6 +108,7 @@ class Configuration:
         self.refit_mode = conf.get("refit_mode", "broadcast")
         self.collector_async = bool(conf.get("collector_async", False))
         self.refit_lag = int(conf.get("refit_lag", 1))
+        self.collector_pipelined = bool(conf.get("collector_pipelined", True))
         self.reserve_sms = int(conf.get("reserve_sms", 16))
         self.drop_coincident = bool(conf.get("drop_coincident", True))
         self.surrogate_precision = conf.get("surrogate_precision", "f64")

@@ -21,7 +21,7 @@ import torch
 
 from . import _lib as L
 from .chains import ChainBlock, Proposal, Trace
-from .collector import AsyncCollector, Collector
+from .collector import AsyncCollector, Collector, PipelinedCollector
 from .device import DeviceProblem
 from .lhs_normal import lhs_normal
 
@@ -143,7 +143,9 @@ class LockstepSampler:
         refits0 = col.no_refits if col is not None else 0
         done, swapped = 0, False
         use_async = collects and self.conf.collector_async and self.truth is not None
-        acol = AsyncCollector(col, self.device, lag=self.conf.refit_lag) if use_async else None
+        acol = None
+        if use_async:
+            acol = (PipelinedCollector if self.conf.collector_pipelined else AsyncCollector)(col, self.device, lag=self.conf.refit_lag)
         traces, b = [], 0
         main = torch.cuda.current_stream(self.device)
         while done < n_steps:

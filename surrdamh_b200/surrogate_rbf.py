@@ -277,6 +277,94 @@ class Surrogate_update:
         pack_out[self.pack_layout(n0, d, m)[3]:].copy_(status)      # the status always describes THIS round
         return pack_out
 
+    # ---- the same round in two stages (PipelinedCollector) -------------------------------------------------------------
+    # thin_stage: the cheap, strictly sequential part (candidates, greedy thinning, compaction -- one SM for ~1 ms);
+    # solve_stage: the dense solve, which depends on the thinned set of ITS round only.  Round b+1 can therefore be
+    # thinned while round b is still being solved, and the solves of consecutive rounds can run on different ranks.
+    def result_layout(self):
+        n, d, m = int(self.no_keep), self.no_parameters, self.no_observations
+        o_s = ((n + d + 1) * m + 15) // 16 * 16
+        return o_s, o_s + 16
+
+    def new_result(self):
+        """[COEFS | status]: what the rank on solve duty broadcasts."""
+        return torch.zeros((self.result_layout()[1],), dtype=torch.float64, device="cuda")
+
+    def new_thin_state(self):
+        """(X [no_keep x d], Y [no_keep x m], meta [4] = rows kept, snapshots offered): the center set after a round."""
+        n, d, m = int(self.no_keep), self.no_parameters, self.no_observations
+        return (torch.zeros((n, d), dtype=torch.float64, device="cuda"), torch.zeros((n, m), dtype=torch.float64, device="cuda"),
+                torch.zeros((4,), dtype=torch.float64, device="cuda"))
+
+    def thin_stage(self, X0, Y0, gathered, world, quota, Xn, Yn, meta):
+        n0, d, m = int(self.no_keep), self.no_parameters, self.no_observations
+        ncand = n0 + world * quota
+        tb = getattr(self, "_thin_bufs", None)
+        if tb is None or tb["key"] != (ncand, n0):
+            tb = dict(key=(ncand, n0), X=torch.empty((ncand, d), dtype=torch.float64, device="cuda"),
+                      Y=torch.empty((ncand, m), dtype=torch.float64, device="cuda"),
+                      alive=torch.empty((ncand,), dtype=torch.uint8, device="cuda"),
+                      keep=torch.empty((ncand,), dtype=torch.uint8, device="cuda"),
+                      work=torch.empty((L.lib().sdb_rbf_thin_work(ncand),), dtype=torch.float64, device="cuda"),
+                      total=torch.zeros((1,), dtype=torch.int64, device="cuda"),
+                      count=torch.zeros((1,), dtype=torch.int32, device="cuda"))
+            self._thin_bufs = tb
+        h, st = L.lib(), L.stream_handle()
+        L.check(h.sdb_round_candidates(L.ptr(X0), L.ptr(Y0), n0, L.ptr(gathered), world, quota, d, m, L.ptr(tb["X"]), L.ptr(tb["Y"]),
+                                       L.ptr(tb["alive"]), L.ptr(tb["total"]), st))
+        L.check(h.sdb_rbf_thin_masked(L.ptr(tb["X"]), ncand, d, n0, L.ptr(tb["alive"]), 0, L.ptr(tb["keep"]), L.ptr(tb["work"]), st))
+        L.check(h.sdb_rows_compact(L.ptr(tb["X"]), L.ptr(tb["Y"]), L.ptr(tb["keep"]), ncand, d, m, n0, L.ptr(Xn), L.ptr(Yn),
+                                   L.ptr(tb["count"]), st))
+        meta.zero_()
+        meta[0] = tb["count"][0].to(torch.float64)
+        meta[1] = tb["total"][0].to(torch.float64)
+
+    def solve_stage(self, X, Y, meta, result):
+        """Dense solve of the rows (X, Y) into result = [COEFS | status]; status[0] != 0: keep the previous surrogate."""
+        n0, d, m = int(self.no_keep), self.no_parameters, self.no_observations
+        sb = getattr(self, "_solve_bufs", None)
+        if sb is None or sb["key"] != (n0, d, m):
+            # fixed staging buffers: one CUDA graph of the solver serves every slot of the collector's rings
+            sb = dict(key=(n0, d, m), X=torch.empty((n0, d), dtype=torch.float64, device="cuda"),
+                      Y=torch.empty((n0, m), dtype=torch.float64, device="cuda"),
+                      C=torch.empty((n0 + d + 1, m), dtype=torch.float64, device="cuda"),
+                      info=torch.zeros((4,), dtype=torch.int32, device="cuda"))
+            self._solve_bufs = sb
+        sb["X"].copy_(X)
+        sb["Y"].copy_(Y)
+        sb["info"].zero_()
+        self._solve_dense(sb["X"], sb["Y"], sb["C"], n0, sb["info"])
+        o_s, _ = self.result_layout()
+        bad = (sb["info"][0] != 0) | (meta[0] != n0) | ~torch.isfinite(sb["C"]).all()
+        result[:(n0 + d + 1) * m].copy_(sb["C"].reshape(-1))
+        status = result[o_s:o_s + 16]
+        status.zero_()
+        status[0] = bad.to(torch.float64)
+        status[1] = sb["info"][0].to(torch.float64)
+        status[2:4] = meta[0:2]
+
+    def assemble(self, result, X, Y, pack_prev, pack_out):
+        """pack_out = [COEFS of result | X | Y | status], or a copy of pack_prev when the round's solve failed."""
+        n0, d, m = int(self.no_keep), self.no_parameters, self.no_observations
+        o_c, o_x, o_y, o_s, _ = self.pack_layout(n0, d, m)
+        r_s, _ = self.result_layout()
+        status = result[r_s:r_s + 16]
+        pack_out[o_c:o_c + (n0 + d + 1) * m].copy_(result[:(n0 + d + 1) * m])
+        pack_out[o_x:o_x + n0 * d].copy_(X.reshape(-1))
+        pack_out[o_y:o_y + n0 * m].copy_(Y.reshape(-1))
+        torch.where(status[0] != 0, pack_prev, pack_out, out=pack_out)
+        pack_out[o_s:].copy_(status)                                   # the status always describes THIS round
+
+    def model_of_pack(self, pack):
+        coefs, X, _, _ = self.pack_views(pack)
+        return DeviceModel(L.MODEL_RBF, kernel_type=self.kernel_type, coefs=coefs, centers=X, d=self.no_parameters,
+                           m=self.no_observations)
+
+    def adopt_thin_state(self, X, Y):
+        """The updater's rows := a thinned center set (the end of a pipelined stage)."""
+        self._par, self._obs = X, Y
+        self.no_processed = X.shape[0]
+
     def update(self):
         mo, n = self.update_device()
         self.last_info = self._info.cpu().numpy()

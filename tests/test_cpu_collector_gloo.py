@@ -181,3 +181,104 @@ def test_collector_fixed_shape_world2(mode):
     assert (n0, n1) == {"broadcast": (5, 0), "rotate": (3, 2), "replicated": (5, 5)}[mode]
     want = [((r) % 3) + ((r + 1) % 3) for r in range(5)]     # snapshots offered per round: both ranks' counts
     assert t0 == want and t1 == want
+
+
+class PipeStub(FixedStub):
+    """CPU stand-in for the staged interface (thin_stage / solve_stage / assemble): the thin stage folds the round's
+    snapshots into a running checksum held in X[0, 0]; the solve stage 'fits' COEFS[0, 0] = 2 * that checksum and fails
+    on demand."""
+
+    def __init__(self, d, m, no_keep, rank, fail_rounds=()):
+        super().__init__(d, m, no_keep, rank)
+        self.fail_rounds, self.solved, self.thinned = set(fail_rounds), [], 0
+
+    def new_thin_state(self):
+        return (torch.zeros((self.no_keep, self.d), dtype=torch.float64), torch.zeros((self.no_keep, self.m), dtype=torch.float64),
+                torch.zeros((4,), dtype=torch.float64))
+
+    def new_result(self):
+        return torch.zeros((self.no_keep + 16,), dtype=torch.float64)
+
+    def thin_stage(self, X0, Y0, gathered, world, quota, Xn, Yn, meta):
+        g = gathered.view(world, quota + 1, self.d + self.m)
+        tot, k_all = 0.0, 0
+        for r in range(world):
+            k = int(g[r, 0, 0])
+            tot += float(g[r, 1:1 + k].sum()) + 1000.0 * k
+            k_all += k
+        Xn.copy_(X0)
+        Yn.copy_(Y0)
+        Xn[0, 0] += tot
+        meta.zero_()
+        meta[0], meta[1] = self.no_keep, k_all
+        self.thinned += 1
+
+    def solve_stage(self, X, Y, meta, result):
+        idx = len(self.solved)
+        result.zero_()
+        result[0] = 2.0 * float(X[0, 0])
+        result[-16] = 1.0 if self.round_of_next_solve in self.fail_rounds else 0.0
+        result[-16 + 3] = meta[1]
+        self.solved.append(self.round_of_next_solve)
+
+    def assemble(self, result, X, Y, pack_prev, pack_out):
+        coefs, Xp, Yp, status = self.pack_views(pack_out)
+        coefs.view(-1).copy_(result[:self.no_keep])
+        Xp.copy_(X)
+        Yp.copy_(Y)
+        if float(result[-16]) != 0.0:
+            pack_out.copy_(pack_prev)
+        self.pack_views(pack_out)[3].copy_(result[-16:])
+
+    def model_of_pack(self, pack):
+        coefs, X, _, _ = self.pack_views(pack)
+        return StubModel(coefs, X)
+
+
+def _worker_pipe(rank, world, port, mode, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from surrdamh_b200.collector import Collector, PipelinedCollector
+    d, m, n0 = 2, 1, 5
+    upd = PipeStub(d, m, n0, rank, fail_rounds=(3,))
+    col = Collector(upd, "rbf", d, m, rank=rank, world=world, snapshots_per_refit=4, refit_mode=mode, device="cpu")
+    col.model_factory = lambda k, coefs, extra: StubModel(coefs, extra)
+    col.select = lambda trace, K: trace                     # the test hands in ready-made blocks
+    start = torch.arange(n0 * d, dtype=torch.float64).view(n0, d) if (rank == 0 or mode == "replicated") else torch.zeros((n0, d), dtype=torch.float64)
+    col.model = StubModel(torch.zeros((n0 + d + 1, m), dtype=torch.float64), start)
+    pc = PipelinedCollector(col, "cpu", lag=2)
+    seen = []
+    for rnd in range(6):
+        block = torch.zeros((col.quota + 1, d + m), dtype=torch.float64)
+        k = (rnd + rank) % (col.quota + 1)
+        block[0, 0] = k
+        block[1:1 + k] = 10.0 * rank + rnd + 1.0
+        upd.round_of_next_solve = rnd
+        pc.submit(rnd, block, 1, None, rnd)
+        ev, model = pc.result(rnd)
+        seen.append((float(model.coefs[0, 0]), float(model.centers[0, 0]), float(model.centers[1, 1])))
+    pc.close()
+    out[rank] = (seen, upd.solved, upd.thinned, float(col.model.coefs[0, 0]), [s[1] for s in col.poll_status(wait=True)])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["broadcast", "rotate", "replicated"])
+def test_pipelined_collector_world2(mode):
+    """PipelinedCollector over gloo: every rank runs the thin stage of every round, the solve runs on the rank on duty
+    only, ONE broadcast per round hands [COEFS | status] to the others, a failed solve (round 3) leaves the previous
+    round's model in place on every rank while the thinned state keeps evolving."""
+    world, port = 2, _free_port()
+    mgr = tmp.Manager()
+    out = mgr.dict()
+    tmp.spawn(_worker_pipe, args=(world, port, mode, out), nprocs=world, join=True)
+    (s0, solved0, th0, last0, st0), (s1, solved1, th1, last1, st1) = out[0], out[1]
+    assert s0 == s1 and last0 == last1                       # identical models on both ranks after every round
+    assert th0 == th1 == 6                                   # the thin stage is replicated
+    assert (solved0, solved1) == {"broadcast": ([0, 1, 2, 3, 4, 5], []), "rotate": ([0, 2, 4], [1, 3, 5]),
+                                  "replicated": ([0, 1, 2, 3, 4, 5], [0, 1, 2, 3, 4, 5])}[mode]
+    coefs = [c for c, _, _ in s0]
+    assert all(c == 2.0 * x for (c, x, _) in s0)             # COEFS and centers of a model belong to the same round ...
+    assert coefs[3] == coefs[2] and coefs[4] > coefs[3]      # ... the failed round 3 shows round 2's model, round 4 moved on
+    assert all(y == 3.0 for _, _, y in s0)                   # rank 0's start state reached every rank (centers[1, 1] = 3)
+    assert st0 == st1 == [0, 0, 0, 1, 0, 0]                  # the status log names the failed round

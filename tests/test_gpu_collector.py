@@ -252,3 +252,28 @@ def test_async_collector_is_the_synchronous_schedule_with_a_lag(L):
     assert runs[0][3] == runs[2][3] == 3 + 10
     # same number of rounds as the synchronous schedule, different (lagging) surrogates -> different trajectories
     assert not np.array_equal(runs[0][0], runs[2][0])
+
+
+def test_pipelined_collector_equals_the_serial_asynchronous_one(L):
+    """collector_pipelined (thin stage and solve stage on streams of their own, PipelinedCollector) against the serial
+    asynchronous round with the same lag: the same thinning of the same candidates and the same dense solve, so the
+    chains, the counters and the final surrogate agree bit for bit; lag 1 and lag 3 (several rounds in flight)."""
+    from surrdamh_b200.sampler import LockstepSampler
+    stages = [{"type": "MH", "max_samples": 60, "time_limit": 600, "proposal_std": 1.0, "surrogate_is_updated": True},
+              {"type": "DAMH", "max_samples": 240, "time_limit": 600, "proposal_std": 1.0, "surrogate_is_updated": True},
+              {"type": "DAMH", "max_samples": 60, "time_limit": 600, "proposal_std": 1.0, "surrogate_is_updated": True}]
+    kw = dict(surrogate_type="rbf", surr_solver_parameters={"kernel_type": 1},
+              surr_updater_parameters={"kernel_type": 1, "solver_type": "nullspace", "no_keep": 300}, refit_every=20,
+              snapshots_per_refit=128, samplers_list=stages, collector_async=True)
+    for lag in (1, 3):
+        runs = []
+        for piped in (True, False):
+            smp = LockstepSampler(_conf(collector_pipelined=piped, refit_lag=lag, **kw), no_chains=300)
+            smp.run()
+            assert smp.collector.fixed and smp.collector.updater.round_failures == 0
+            runs.append((smp.block.current_numpy(), smp.block.counters_numpy(), smp.collector.model.coefs.cpu().numpy(),
+                         smp.collector.model.centers.cpu().numpy(), smp.collector.no_refits,
+                         smp.collector.updater.processed_par))
+        for a, b in zip(runs[0], runs[1]):
+            assert np.array_equal(a, b), lag
+        assert np.array_equal(runs[0][3], runs[0][5])            # the updater took over the last round's center set
