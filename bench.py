@@ -861,7 +861,7 @@ def main():
     ap.add_argument("--refit-mode", default="", choices=["", "broadcast", "rotate", "replicated"])
     ap.add_argument("--lag", type=int, default=1, help="blocks of lag of the asynchronous collector (weak-scaling record)")
     ap.add_argument("--strong-lag", type=int, default=0, help="the same for the strong-scaling record (0: the number of GPUs)")
-    ap.add_argument("--reserve-sms", type=int, default=16, help="SMs the chain kernel leaves to the asynchronous collector's kernels")
+    ap.add_argument("--reserve-sms", type=int, default=15, help="SMs the chain kernel leaves to the asynchronous collector's kernels")
     ap.add_argument("--profile", type=int, default=0, help="run this many bench steps inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -21,7 +21,7 @@ ADDITIVE keys of this implementation (ignored by the reference, never renames):
   refit_lag            blocks of lag of the asynchronous collector (default 1)
   collector_pipelined  (with collector_async, default true) the round runs as two pipelined stages -- thinning on every
                        rank, the dense solve on the rank on duty -- so consecutive rounds overlap (PipelinedCollector)
-  reserve_sms          SMs the chain kernel leaves free for the asynchronous collector's kernels (default 16; the
+  reserve_sms          SMs the chain kernel leaves free for the asynchronous collector's kernels (default 15; the
                        chain CTAs own their SMs, so the refit needs SMs of its own to run beside them)
   surrogate_precision  'f64' (default, the reference's arithmetic) | 'f32': an RBF surrogate is evaluated on the FP32
                        pipe inside the chain kernel (stage 1 only screens; stage 2 keeps the chain exact)
@@ -109,7 +109,7 @@ class Configuration:
         self.collector_async = bool(conf.get("collector_async", False))
         self.refit_lag = int(conf.get("refit_lag", 1))
         self.collector_pipelined = bool(conf.get("collector_pipelined", True))
-        self.reserve_sms = int(conf.get("reserve_sms", 16))
+        self.reserve_sms = int(conf.get("reserve_sms", 15))
         self.drop_coincident = bool(conf.get("drop_coincident", True))
         self.surrogate_precision = conf.get("surrogate_precision", "f64")
         if self.surrogate_precision not in ("f64", "f32"):
