@@ -28,6 +28,13 @@ the same peak; `cpu_baseline` = the REFERENCE's own Algorithm_DAMH.run (unmodifi
 oracle/_ref, CSV output on) on the host cores -- the numpy oracle when that copy is absent;
 `other_workloads` (N = 1) = short cfg2 / cfg5 records.  NCCL's INFO log goes to stderr.
 """
+import os as _os
+
+# more hardware launch queues than the default 8: the collector adds ~8 streams (thin / solve / assemble lanes, the
+# refit's side streams, one NCCL stream per communicator) and two streams sharing a queue serialise -- a KB-sized
+# all-gather then waits behind a 14 ms chain kernel.  Must be set before the CUDA context exists.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import argparse
 import json
 import multiprocessing as mp
@@ -455,6 +462,7 @@ class Run:
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
+        self.base_event = t0
         for _ in range(n_steps):
             self.one_block(True, host_io)
         self.drain()             # the last collector rounds belong to the timed region
@@ -496,11 +504,23 @@ class Run:
         launches = int(L.lib().sdb_launch_count(1))
         kern = [(a.elapsed_time(b), sw) for a, b, sw in self.kern_ev]
         rounds = [a.elapsed_time(b) for a, b in (self.acol.round_events if self.acol is not None else self.round_ev)]
+        if os.environ.get("SDB_TIMELINE") and getattr(self.acol, "stage_events", None):
+            # development: device times (ms since the start of the timed region) of every block and round of this rank
+            base = self.base_event
+            tl = {"rank": self.rank, "chains": self.C,
+                  "blocks": [[base.elapsed_time(a), base.elapsed_time(b)] for a, b, _ in self.kern_ev],
+                  "rounds": [[base.elapsed_time(e) if e is not None else None for e in (t0_, g, t, s_, m_)]
+                             for t0_, t, s_, m_, g in self.acol.stage_events],
+                  "columns": "blocks: chain kernel start, end; rounds: start, gathered, thinned, solved (duty rank), assembled"}
+            with open("%s_c%d_rank%d.json" % (os.environ["SDB_TIMELINE"], self.C, self.rank), "w") as f:
+                json.dump(tl, f)
         stages = None
         if getattr(self.acol, "stage_events", None):
             ev = self.acol.stage_events
-            solved = [t.elapsed_time(s_) for _, t, s_, _ in ev if s_ is not None]
-            stages = {"thin": float(np.mean([a.elapsed_time(t) for a, t, _, _ in ev])),
+            solved = [t.elapsed_time(s_) for _, t, s_, _, _ in ev if s_ is not None]
+            stages = {"thin": float(np.mean([a.elapsed_time(t) for a, t, _, _, _ in ev])),
+                      "select_and_gather": float(np.mean([a.elapsed_time(g) for a, _, _, _, g in ev])),
+                      "assemble_after_thin": float(np.mean([t.elapsed_time(m_) for _, t, _, m_, _ in ev])),
                       "solve_on_duty_rank": float(np.mean(solved)) if solved else None, "solves_here": len(solved)}
             ev.clear()
         self.kern_ev.clear(); self.round_ev.clear()

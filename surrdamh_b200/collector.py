@@ -371,7 +371,7 @@ class PipelinedCollector(AsyncCollector):
         self.nring = self.lag + 4
         self.slots = None
         self.n_piped = 0
-        self.stage_events = []                          # timed rounds: (start, thinned, solved | None, assembled)
+        self.stage_events = []                          # timed rounds: (start, thinned, solved | None, assembled, gathered)
         self.last = None                                # slot of the newest round
 
     # ---- state ---------------------------------------------------------------------------------------------------
@@ -389,6 +389,17 @@ class PipelinedCollector(AsyncCollector):
         s0["Y"].copy_(Y0)
         s0["pack"].copy_(cur)
         self.last = self.nring - 1
+        if self.cuda:
+            # Prime the solve path on EVERY rank now (scratch allocation, module loads, CUDA-graph capture of the solver): a
+            # rank whose first solve duty came in the middle of a run stalled for ~200 ms (measured, 4 GPUs), and with it every
+            # other rank at the next all-gather.
+            ev = self.thin.record()
+            with self.solve:
+                self.solve.wait(ev)
+                scratch = self.slots[0]
+                scratch["meta"][0] = float(int(up.no_keep))
+                for _ in range(2):
+                    up.solve_stage(s0["X"], s0["Y"], scratch["meta"], scratch["result"])
 
     def submit(self, b, trace, K, chain_done_event, step, timed=False):
         col, up = self.col, self.col.updater
@@ -405,6 +416,7 @@ class PipelinedCollector(AsyncCollector):
             t0 = self.thin.record(timing=True) if timed else None
             block = col.select(trace, K)
             gathered = col.gather(block, self.ggroup)
+            ev_g = self.thin.record(timing=True) if timed else None
             up.thin_stage(prev["X"], prev["Y"], gathered.reshape(-1), col.world, col.quota, cur["X"], cur["Y"], cur["meta"])
             ev_t = self.thin.record(timing=timed)
         duty = col.duty_rank(col.no_refits)
@@ -425,7 +437,7 @@ class PipelinedCollector(AsyncCollector):
             col._queue_status(up.pack_views(cur["pack"])[3])
             ev_m = self.asm.record(timing=timed)
         if timed:
-            self.stage_events.append((t0, ev_t, ev_s, ev_m))
+            self.stage_events.append((t0, ev_t, ev_s, ev_m, ev_g))
             self.round_events.append((t0, ev_m))
         self.last = (self.last + 1) % self.nring
         self.n_piped += 1
