@@ -618,9 +618,33 @@ def f32_decision_check(w, run, dev):
                                        "either way, so the sampled distribution is the exact posterior in both runs"}
 
 
+def solve_alone_ms(run, reps=5):
+    """The collector's dense solve of the current center set, alone on the GPU (default stream), ms per solve."""
+    torch, up = run.torch, run.updater
+    n0 = int(up.no_keep)
+    if up._par.shape[0] != n0 or not hasattr(up, "solve_stage"):
+        return None
+    run.drain()
+    torch.cuda.synchronize(run.dev)
+    X, Y = up._par.clone(), up._obs.clone()
+    meta = torch.tensor([float(n0), 0.0, 0.0, 0.0], dtype=torch.float64, device=run.dev)
+    res = up.new_result()
+    for _ in range(2):
+        up.solve_stage(X, Y, meta, res)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        up.solve_stage(X, Y, meta, res)
+    b.record()
+    b.synchronize()
+    return a.elapsed_time(b) / reps
+
+
 def kernel_name(w):
     if w["surrogate"] == "poly" and w["d"] == 2 and w["m"] == 1 and not os.environ.get("SDB_NO_LEAN"):
         return "chain_lean_kernel<%d,true>" % w["degree"]
+    if w["surrogate"] == "rbf" and w.get("centers", 0) >= 1024 and not os.environ.get("SDB_NO_WT"):
+        return "chain_kernel<%d,%d,0,true>" % (w["d"], w["m"])      # warp-owned chains (csrc/sdb_chain_wt.cu)
     return "chain_kernel<%d,%d>" % (w["d"], w["m"])
 
 
@@ -632,11 +656,19 @@ def roofline_of(w, run, rec, peak_tf, peak3_tf, headline):
     flops_launch = float(C_) * (K + frac_sw) * per_point
     achieved = flops_launch / (avg_ms * 1e-3) / 1e12
     out = {"bound": "fp64-pipe", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-           "traffic": 123539712 if headline else None, "kernel": kernel_name(w), "kernel_ms": avg_ms,
+           "traffic": 131635456 if headline else None, "kernel": kernel_name(w), "kernel_ms": avg_ms,
            "kernel_share_of_step": avg_ms * len(rec["kern"]) / (rec["ms_per_step"] * rec["steps"]), "flops_per_launch": flops_launch}
+    plan = run.blk.plan("DAMH", run.state["sur"], run.truth, run.prop)
+    if run.reserve_sms and plan["lanes_per_chain"] == 0:
+        from surrdamh_b200 import _lib as L
+        sms = L.device_info()["sm_count"]
+        used = max(1, sms - run.reserve_sms)
+        out.update({"sms_used": used, "sms_total": sms, "frac_of_the_sms_used": achieved / (peak_tf * used / sms),
+                    "sms_note": "the launch leaves %d SMs to the asynchronous collector's kernels; `frac` is against the peak of "
+                                "the WHOLE GPU" % run.reserve_sms})
     if headline:
         out.update({"traffic_note": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the ncu --set full capture in "
-                                    "profiles/r01_chain_kernel_ncu.md; algorithmic bytes = C*K*25 B trace + state = 1.05e8",
+                                    "profiles/r02_chain_kernel_ncu.md; algorithmic bytes = C*K*25 B trace + state = 1.05e8",
                     "peak_three_register_fma": peak3_tf,
                     "peak_source": "sdb_fp64_probe (8 independent DFMA chains/thread), measured live in this run; "
                                    "MEASURED_PEAKS.json has no FP64 entry"})
@@ -803,11 +835,15 @@ def run_ours(args):
                                        + "surrogate of round b used from block b+%d; round_ms = latency from the end of "
                                          "the block to the assembled model, on the %d SMs the chain kernel leaves free"
                                        % (run.lag + 1, run.reserve_sms))}
-        out["roofline_refit"] = {"bound": "fp64-tensor (DMMA)", "achieved": flop / (round_ms * 1e-3) / 1e12, "peak": peak_tf,
-                                 "unit": "TFLOP/s", "frac": flop / (round_ms * 1e-3) / 1e12 / peak_tf, "flops_per_round": flop,
-                                 "round_ms": round_ms,
-                                 "note": "n^3/3 flop of the Cholesky over the WHOLE collector round (exchange, thinning, build, "
-                                         "solve), same live FP64 peak; at n = 4096 the round is latency-bound (DESIGN.md 4.2)"}
+        alone_ms = solve_alone_ms(run) if w.get("solver_type") in ("nullspace", "direct") else None
+        ref_ms = alone_ms if alone_ms else round_ms
+        out["roofline_refit"] = {"bound": "fp64-tensor (DMMA)", "achieved": flop / (ref_ms * 1e-3) / 1e12, "peak": peak_tf,
+                                 "unit": "TFLOP/s", "frac": flop / (ref_ms * 1e-3) / 1e12 / peak_tf, "flops_per_round": flop,
+                                 "solve_alone_ms": alone_ms, "round_ms": round_ms,
+                                 "note": "n^3/3 flop of the Cholesky over the dense solve (system build + null-space projection + "
+                                         "factorisation + substitutions) timed ALONE on the whole GPU after the run, same live FP64 "
+                                         "peak; at n = 4096 the solve is latency-bound (DESIGN.md 4.2).  Inside the run it shares "
+                                         "the GPU with the chain kernel: collector.stages_ms"}
     if fp32 is not None:
         out["fp32_surrogate"] = fp32
     if strong is not None:

@@ -126,9 +126,10 @@ typedef struct sdb_chain_args {
     int32_t algorithm; /* SDB_ALG_* */
     int32_t phase;     /* SDB_PHASE_* */
     int32_t n_steps;   /* K lockstep steps in this launch (1 for the split phases) */
-    int32_t lanes_per_chain; /* 1,2,4,8,16 or 32 threads cooperating on one chain; 0 = library picks (with an RBF
-                              * surrogate: warp-owned chains -- a warp owns up to 32 chains, one per lane, and all 32 lanes
-                              * split the centers of every evaluation; sdb_chain_plan then reports lanes_per_chain 0) */
+    int32_t lanes_per_chain; /* 1,2,4,8,16 or 32 threads cooperating on one chain; 0 = library picks: with an RBF
+                              * surrogate of >= 1024 centers warp-owned chains (a warp owns up to 32 chains, one per lane,
+                              * and all 32 lanes split the centers of every evaluation; sdb_chain_plan then reports
+                              * lanes_per_chain 0), else lane groups.  < 0 forces the warp-owned shape. */
     int32_t refresh_pre;     /* recompute pre_u = log posterior(surrogate(u)) first (surrogate was swapped) */
     int32_t have_G;          /* PREPARE: G_u already holds G(u) (host-evaluated); else the device model fills it */
     sdb_problem problem;

@@ -345,7 +345,11 @@ static int plan(const sdb_chain_args *a, int *L_out, int *threads_out, int *bloc
     int L = a->lanes_per_chain;
     static const bool no_wt = getenv("SDB_NO_WT") != nullptr;
     if (wt_out) *wt_out = 0;
-    if (L <= 0 && rbf_sur && !no_wt) {
+    // Warp-owned chains pay a fixed cost per pass (shuffling the group's points in, the 32-lane tree out) and bind a chain
+    // to its warp for the whole launch; with few centers per lane (cfg5: 500 centers = 16 per lane) the lane-group shape
+    // below is faster (measured 8.7 against 10.5 ms).  lanes_per_chain < 0 forces the warp-owned shape.
+    static const int wt_min_centers = getenv("SDB_WT_MIN_CENTERS") ? atoi(getenv("SDB_WT_MIN_CENTERS")) : 1024;
+    if (rbf_sur && !no_wt && (L < 0 || (L == 0 && a->surrogate.n_centers >= wt_min_centers))) {
         // warp-owned chains: 16-warp CTAs, one per SM and wave; the chains are dealt evenly to the warps of the grid (up to
         // 32 each), so every sub-partition carries the same number of pairs whatever C is.  65 536 chains: 148 CTAs,
         // 27 or 28 chains per warp, one wave -- against 293 CTAs of 14 warps (3 or 4 per sub-partition) in two waves.
