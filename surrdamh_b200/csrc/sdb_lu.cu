@@ -64,7 +64,10 @@ __global__ void __launch_bounds__(LU_T, 1)
     __shared__ double win_val;
     __shared__ int win_row, win_slot;
     constexpr int TS = W + 2;                           // even: (row, even column) is 16-byte aligned; 33 i mod 8 banks
-    constexpr int CH = 16, NCH = (W + CH - 1) / CH;     // elimination work item = (row, 16-column chunk)
+    // elimination work item = (row, 16-column chunk); a chunk must not reach past the row: with W = 8 (sub-panels of more than
+    // ~20 000 rows) a 16-wide chunk read AND WROTE BACK the first columns of the next slot's row, racing with that row's own
+    // thread (backward error 5e-7 at n = 32768, found by the round-2 refit sweep against np.linalg.solve)
+    constexpr int CH = W < 16 ? W : 16, NCH = (W + CH - 1) / CH;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row0 = j0 + rank * rpc;                       // first row of this CTA
     const int nloc = max(0, min(rpc, N - row0));            // rows it really holds
@@ -387,8 +390,10 @@ static lu_base_plan lu_plan_base(int rows) {
     p.CL = lu_cluster_size();
     p.rpc = (rows + p.CL - 1) / p.CL;
     const int widths[4] = {64, 32, 16, 8};
+    static const int wmax = getenv("SDB_LU_BASE_MAX") ? atoi(getenv("SDB_LU_BASE_MAX")) : 64;   // tests: force the narrow bases
     for (int k = 0; k < 4; ++k) {
         p.W = widths[k];
+        if (p.W > wmax && k < 3) continue;
         p.smem = (size_t)p.rpc * (p.W + 2) * sizeof(double) + (size_t)p.rpc * 2 * sizeof(int) + 16;
         if (p.smem <= budget) return p;
     }

@@ -357,3 +357,20 @@ def test_paired_tma_update_on_ragged_sizes_in_a_subprocess(L, group):
                         "test_rbf_nullspace_cholesky_matches_direct or test_rbf_nullspace_large_paired_update"],
                        cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0 and "2 passed" in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.parametrize("wmax", ["8", "16"])
+def test_lu_narrow_base_panels_in_a_subprocess(L, wmax):
+    """Sub-panels of more than ~20 000 / ~10 000 rows fall back to 8- / 16-column base cases of the cluster panel kernel (shared-memory
+    budget), sizes no parity test reaches directly (n = 32 768 of BASELINE configs[3]).  The base width is read once per
+    process, so a child process with SDB_LU_BASE_MAX=8 / 16 re-runs the LAPACK parity cases (pivot sequence, factors, residual)
+    through the narrow bases.  (Round 2: the 8-column base eliminated in 16-wide chunks that reached into the next row.)"""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, SDB_LU_BASE_MAX=wmax)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_fit.py", "-k",
+                        "test_lu_solve_matches_lapack or test_lu_singular_reports_info"],
+                       cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0 and "15 passed" in r.stdout, r.stdout[-2000:]
