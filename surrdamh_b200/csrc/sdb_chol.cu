@@ -634,7 +634,8 @@ __global__ void __launch_bounds__(NS_T, 2) ns_finish_kernel(const double *__rest
 static bool ns_kernel_supported(int kt) { return kt == 0 || kt == 1 || kt == 4 || kt == 5 || kt == 6; }
 
 // leading dimension of the system in the work buffer: room for the m right-hand-side rows below row n
-static inline int64_t ns_ld(int64_t n, int d, int m) { return n + (m > d + 1 ? m : d + 1); }
+// even: the column stride of the work matrix is then a multiple of 16 bytes, which a TMA tensor map requires (sdb_syrk_tma_kernel)
+static inline int64_t ns_ld(int64_t n, int d, int m) { return (n + (m > d + 1 ? m : d + 1) + 1) & ~(int64_t)1; }
 
 static int ns_enqueue(cudaStream_t st, double *S, int64_t ld, int n, int d, int m, int kernel_type, double *F, double *COEFS,
                       double *vec, int32_t *d_info) {
@@ -797,7 +798,7 @@ static int ns_enqueue(cudaStream_t st, double *S, int64_t ld, int n, int d, int 
                     const int kb = 64 * (G - 1);
                     const double *Lp = A + (int64_t)(k0 - kb) * ld + (k0 + 128);      // rows from k0+128, columns k0-kb .. k0+63
                     SDB_CUDA(cudaStreamWaitEvent(aux, ev_trsm[kp & 3], 0));
-                    if (rest - 64 >= big_min || kb + h > 256) rc = sdb_syrk_big_update(aux, restx - 64, rest - 64, kb + h, Lp, Lp, A22 + (int64_t)64 * ld + 64, ld);
+                    if (rest - 64 >= big_min || kb + h > 256) rc = sdb_syrk_big_update(aux, restx - 64, rest - 64, kb + h, Lp, Lp, A22 + (int64_t)64 * ld + 64, ld, S, (int64_t)n + (d + 1) + m);
                     else rc = sdb_syrk_k64_update(aux, restx - 64, rest - 64, kb + h, Lp, Lp, A22 + (int64_t)64 * ld + 64, ld);
                     if (rc) return rc;
                     issued = true;

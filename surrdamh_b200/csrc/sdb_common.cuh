@@ -138,6 +138,15 @@ __device__ __forceinline__ void sdb_bulk_g2s(void *smem_dst, const void *gmem_sr
                  : "memory");
 }
 
+// 2-D tensor-map TMA: one box of the mapped tensor, starting at element coordinates (c0 = inner, c1 = outer), into shared memory
+// (128-byte aligned), completion by transaction count on `bar`.  `tmap` is a __grid_constant__ kernel parameter.
+__device__ __forceinline__ void sdb_tensor_g2s_2d(void *smem_dst, const void *tmap, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     sdb_smem_u32(smem_dst)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(sdb_smem_u32(bar))
+                 : "memory");
+}
+
 // One elected thread stages `bytes` (a multiple of 16, both pointers 16-byte aligned) in
 // pieces of at most 32 KiB, raising the barrier's transaction count piece by piece.  The
 // caller arrives on `bar` once after its last piece; the phase completes when that arrival

@@ -11,6 +11,10 @@
 // fit (sdb_fit.cu).  Tile 128 x 64 x 8, 256 threads = 8 warps (4 x 2), warp tile 32 x 32,
 // two-stage shared-memory pipeline, register prefetch of the next k-slab.
 #pragma once
+#include <string.h>
+
+#include <cuda.h>      // CUtensorMap and its enums only; cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint (no -lcuda)
+
 #include "sdb_common.cuh"
 
 #define GM_BM 128
@@ -425,22 +429,37 @@ static inline int sdb_gemm_skinny64_launch(cudaStream_t st, int M, int N, int K,
 #endif
 #define SB_LD (SB_T + 4)    // row stride == 4 (mod 16) doubles: the k-rows tig = 0..3 of a fragment load start 8 banks apart
 
-template <bool LOWER>
+// TM (round 2): the operands are described by ONE 2-D tensor map over the whole work buffer (inner dimension = a column of `ld`
+// doubles, ld padded to an even number so that the column stride is a multiple of 16 bytes) and a ring stage is filled by TWO
+// cp.async.bulk.tensor copies of a 132 x 16 box -- the tile's 128 rows plus the 4 columns of padding that keep the fragment
+// loads conflict-free (box rows land 132 doubles apart, exactly the layout the row-by-row producer builds); rows / columns beyond the
+// buffer are zero-filled by the TMA unit.
+// (ia, ka) / (ib, kb): element coordinates of A(m0 = 0, k = 0) and A2(n0 = 0, k = 0) inside the mapped buffer.
+template <bool LOWER, bool TM>
 static __global__ void __launch_bounds__(256, 1) sdb_syrk_tma_kernel(const double *__restrict__ A, const double *__restrict__ A2,
-                                                                     double *__restrict__ C, int64_t ld, int M, int N, int K) {
+                                                                     double *__restrict__ C, int64_t ld, int M, int N, int K,
+                                                                     const __grid_constant__ CUtensorMap tmap, int ia, int ka, int ib,
+                                                                     int kb) {
     constexpr int SLICE = 2 * SB_KS * SB_LD;                     // doubles per ring stage (A rows, then A2 rows)
     constexpr uint32_t ROW_BYTES = (SB_T + 2) * 8;
     const int m0 = blockIdx.x * SB_T, n0 = blockIdx.y * SB_T;
     if (LOWER && n0 > m0 + SB_T - 1) return;
+    // the ring comes first in dynamic shared memory and the kernel has NO static shared memory, so every stage starts 128-byte
+    // aligned (a tensor-map copy faults on a destination that is not: "illegal instruction"); the barriers follow the ring
     extern __shared__ __align__(128) double sb_sm[];
-    __shared__ __align__(8) uint64_t full[SB_ST], empty[SB_ST];
+    uint64_t *full = (uint64_t *)(sb_sm + (size_t)SB_ST * SLICE), *empty = full + SB_ST;
     typedef double (*slice_t)[SB_LD];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
     const int gid = lane >> 2, tig = lane & 3;
     const int S = K / SB_KS;                                     // K is a multiple of 16 (checked by the launcher)
+    const void *tmap_ptr = &tmap;                                // address of the __grid_constant__ parameter itself (param space)
     const double *Arow = A + m0, *Brow = A2 + n0;
-    const int pa = (int)(((uintptr_t)Arow >> 3) & 1), pb = (int)(((uintptr_t)Brow >> 3) & 1), pl = (int)(ld & 1);
+    // TM: the box must START 16-byte aligned (an odd inner coordinate of an FP64 tensor faults: tools/microbench/mb_tmap.cu), so it
+    // starts at the even coordinate at or one below the tile's first row and the data lands with that shift, like the rows of the
+    // row-by-row producer; ld is even, so the shift is the same for every k-row.
+    const int pa = TM ? (ia & 1) : (int)(((uintptr_t)Arow >> 3) & 1), pb = TM ? (ib & 1) : (int)(((uintptr_t)Brow >> 3) & 1),
+              pl = TM ? 0 : (int)(ld & 1);
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < SB_ST; ++i) { sdb_mbar_init(&full[i], 1); sdb_mbar_init(&empty[i], 8); }
@@ -461,6 +480,17 @@ static __global__ void __launch_bounds__(256, 1) sdb_syrk_tma_kernel(const doubl
     }
     auto issue = [&](int s) {
         uint64_t *bar = &full[s % SB_ST];
+        if (TM) {
+            if (lane == 0) {
+                double *dst = sb_sm + (size_t)(s % SB_ST) * SLICE;
+                sdb_mbar_expect_tx(bar, 2 * SB_KS * SB_LD * 8);
+                sdb_mbar_arrive(bar);
+                sdb_tensor_g2s_2d(dst, tmap_ptr, ia + m0 - pa, ka + s * SB_KS, bar);
+                sdb_tensor_g2s_2d(dst + SB_KS * SB_LD, tmap_ptr, ib + n0 - pb, kb + s * SB_KS, bar);
+            }
+            __syncwarp();
+            return;
+        }
         if (lane == 0) {
             sdb_mbar_expect_tx(bar, 2 * SB_KS * ROW_BYTES);
             sdb_mbar_arrive(bar);
@@ -528,25 +558,66 @@ static __global__ void __launch_bounds__(256, 1) sdb_syrk_tma_kernel(const doubl
             }
 }
 
-static inline int sdb_syrk_tma_launch(cudaStream_t st, int M, int N, int K, const double *A, const double *A2, double *C, int64_t ld) {
-    const int smem = SB_ST * 2 * SB_KS * SB_LD * 8;
+typedef CUresult (*sdb_tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                       const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static inline sdb_tmap_encode_fn sdb_tmap_encoder() {
+    static sdb_tmap_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (sdb_tmap_encode_fn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// base / base_cols: the column-major buffer (leading dimension ld) the operands live in, for the tensor map; nullptr = row-by-row producer
+static inline int sdb_syrk_tma_launch(cudaStream_t st, int M, int N, int K, const double *A, const double *A2, double *C, int64_t ld,
+                                      const double *base = nullptr, int64_t base_cols = 0) {
+    const int smem = SB_ST * 2 * SB_KS * SB_LD * 8 + 128;      // ring + the full / empty barriers
     static bool attr_set = false;
     if (!attr_set) {
-        SDB_CUDA(cudaFuncSetAttribute((const void *)sdb_syrk_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SDB_CUDA(cudaFuncSetAttribute((const void *)sdb_syrk_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SDB_CUDA(cudaFuncSetAttribute((const void *)sdb_syrk_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     dim3 grid((M + SB_T - 1) / SB_T, (N + SB_T - 1) / SB_T);
+    static const int use_tm = getenv("SDB_SYRK_TENSORMAP") ? atoi(getenv("SDB_SYRK_TENSORMAP")) : 1;
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    sdb_tmap_encode_fn enc = sdb_tmap_encoder();
+    if (use_tm && enc && base && (ld & 1) == 0 && (((uintptr_t)base) & 15) == 0 && A >= base && A2 >= base && ld < (1ll << 31)) {
+        const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)base_cols};
+        const cuuint64_t gstr[1] = {(cuuint64_t)ld * 8};
+        const cuuint32_t box[2] = {SB_LD, SB_KS};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) {
+            const int64_t oa = A - base, ob = A2 - base;
+            sdb_count_launch();
+            sdb_syrk_tma_kernel<true, true><<<grid, 256, smem, st>>>(A, A2, C, ld, M, N, K, tm, (int)(oa % ld), (int)(oa / ld), (int)(ob % ld),
+                                                                     (int)(ob / ld));
+            SDB_CUDA(cudaGetLastError());
+            return SDB_OK;
+        }
+    }
     sdb_count_launch();
-    sdb_syrk_tma_kernel<true><<<grid, 256, smem, st>>>(A, A2, C, ld, M, N, K);
+    sdb_syrk_tma_kernel<true, false><<<grid, 256, smem, st>>>(A, A2, C, ld, M, N, K, tm, 0, 0, 0, 0);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
 }
 
 // lower(C) -= A A2^T for a large trailing matrix, K a multiple of 16 (else, or with SDB_SYRK_TMA=0, the rank-K kernel above)
-static inline int sdb_syrk_big_update(cudaStream_t st, int M, int N, int K, const double *A, const double *A2, double *C, int64_t ld) {
+static inline int sdb_syrk_big_update(cudaStream_t st, int M, int N, int K, const double *A, const double *A2, double *C, int64_t ld,
+                                      const double *base = nullptr, int64_t base_cols = 0) {
     if (M <= 0 || N <= 0 || K <= 0) return SDB_OK;
     static const int tma = getenv("SDB_SYRK_TMA") ? atoi(getenv("SDB_SYRK_TMA")) : 1;
-    if (tma && K % SB_KS == 0) return sdb_syrk_tma_launch(st, M, N, K, A, A2, C, ld);
+    if (tma && K % SB_KS == 0) return sdb_syrk_tma_launch(st, M, N, K, A, A2, C, ld, base, base_cols);
     return sdb_gemm_k64_launch<true, true, false>(st, M, N, K, A, A2, C, ld, ld);
 }
 
