@@ -169,3 +169,60 @@ def test_device_statistics_of_a_gpu_chain_match_reference_formulas():
 def L_dev(x):
     from surrdamh_b200 import _lib as L
     return L.dev(np.ascontiguousarray(x))
+
+
+def test_block_io_delivers_every_block_through_pinned_buffers():
+    """surrdamh_b200/host_io.py: the double-buffered host I/O of the bench's end-to-end leg.  Six blocks of a DAMH run with the
+    chains' samples uploaded from pinned memory at the start of every block and the product downloaded on the copy stream: the
+    delivered samples, counters, moments and flags equal what a plain run that synchronises after every block reads back."""
+    torch = pytest.importorskip("torch")
+    from surrdamh_b200.chains import ChainBlock, Proposal, Trace
+    from surrdamh_b200.device import DeviceModel, DeviceProblem
+    from surrdamh_b200.host_io import BlockIO
+    from tests.golden_util import SIMPLE_PROBLEM
+    C_, K, nblk = 700, 9, 6
+    rs = np.random.RandomState(5)
+    centers = rs.standard_normal((200, 2)) * 2 + np.array([5.0, 3.0])
+    coefs = np.zeros((203, 1))
+    coefs[200:, 0] = [1e-4, -5e-5, -1.2e-3]
+    sur, truth = DeviceModel.rbf(coefs, centers, 1), DeviceModel.toy()
+    prop = Proposal(2, [0.4, 0.2])
+
+    def run(piped):
+        # every block restarts from the same uploaded samples (as bench.py's e2e leg does) with fresh random numbers
+        blk = ChainBlock(DeviceProblem(2, **SIMPLE_PROBLEM), C_, seed=3, moments=True)
+        u0 = blk.u.cpu().clone() + torch.from_numpy(rs0.standard_normal((2, C_))) * 0.1
+        tr = [Trace(K, C_, 2, 1, blk.device, snapshots=False, full=False) for _ in range(2)]
+        got = []
+        if piped:
+            io = BlockIO(blk, K)
+            io.u_in.copy_(u0)
+            io.upload(0)
+            for b in range(nblk):
+                io.begin(b)
+                blk.prepare("DAMH", sur, truth)
+                blk.run("DAMH", K, prop, sur, truth, trace=tr[b & 1])
+                io.finish(b, tr[b & 1])
+                io.upload(b + 1)
+                if b >= 1:
+                    got.append({k: v.clone() for k, v in io.result(b - 1).items()})
+            got.append({k: v.clone() for k, v in io.result(nblk - 1).items()})
+            return got
+        for b in range(nblk):
+            blk.u.copy_(u0.cuda())
+            blk.prepare("DAMH", sur, truth)
+            blk.run("DAMH", K, prop, sur, truth, trace=tr[b & 1])
+            torch.cuda.synchronize()
+            got.append({"u": blk.u.cpu().clone(), "counters": blk.counters.cpu().clone(), "moments": blk.moments.cpu().clone(),
+                        "flags": tr[b & 1].flags[:K].cpu().clone()})
+        return got
+
+    rs0 = np.random.RandomState(9)
+    a = run(True)
+    rs0 = np.random.RandomState(9)
+    b_ = run(False)
+    assert len(a) == len(b_) == nblk
+    for i, (x, y) in enumerate(zip(a, b_)):
+        for k in ("u", "counters", "moments", "flags"):
+            assert torch.equal(x[k], y[k]), (i, k)
+    assert int(a[-1]["counters"][0].sum()) > 0
