@@ -43,6 +43,8 @@ def build(force=False, verbose=False):
             return LIB
         raise RuntimeError("nvcc not found and %s is not built" % LIB)
     os.makedirs(OUT_DIR, exist_ok=True)
+    import time
+    t_start = time.time()
     objs, procs = [], []
     for src in sources():
         obj = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + ".o")
@@ -61,6 +63,16 @@ def build(force=False, verbose=False):
     if r.returncode:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
+    try:
+        import json
+        import time
+        ver = subprocess.run([nvcc, "--version"], stdout=subprocess.PIPE, text=True).stdout.strip().splitlines()[-1]
+        with open(os.path.join(OUT_DIR, "build_record.json"), "w") as f:
+            json.dump({"built_at": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), "seconds": round(time.time() - t_start, 1),
+                       "forced": bool(force), "nvcc": ver, "flags": NVCC_FLAGS, "sources": [os.path.basename(s_) for s_ in sources()],
+                       "library": os.path.basename(LIB)}, f, indent=1)
+    except OSError:
+        pass
     return LIB
 
 
