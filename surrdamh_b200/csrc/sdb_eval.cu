@@ -164,6 +164,54 @@ __global__ void __launch_bounds__(256) rbf_eval_kernel(const double *__restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// RBF, many points against tables that fit in shared memory: the chain kernel's warp-owned evaluation (sdb_rbf_points_wt) as
+// a stand-alone kernel.  A persistent grid of one 16-warp CTA per SM stages the tables once (TMA bulk copies); a warp takes
+// 32 consecutive points at a time, one per lane, and all 32 lanes split the centers of every point (passes of 8 points: a center /
+// weight load serves 8 pairs).  Round 2: 0.27 -> 0.40 of the FP64 peak at 1 M points x 4096 centers (profiles/r02_eval_kernels.md).
+// ---------------------------------------------------------------------------------------------------
+template <int D, int M>
+__global__ void __launch_bounds__(512, 1) rbf_eval_wt_kernel(const double *__restrict__ pts, int64_t N, int d_rt, int m_rt,
+                                                             const sdb_model mo, double *__restrict__ out) {
+    constexpr int DD = D ? D : SDB_MAX_D;
+    constexpr int UD = D ? D : 1;
+    constexpr int MM = M ? M : SDB_MAX_M;
+    constexpr int UM = M ? M : 1;
+    const int d = D ? D : d_rt, m = M ? M : m_rt;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bar = (uint64_t *)smem;
+    unsigned char *p = smem + 16;
+    if (threadIdx.x == 0) {
+        sdb_mbar_init(bar, 1);
+        sdb_mbar_fence_init();
+    }
+    __syncthreads();
+    const sdb_smodel sur = sdb_stage_model(mo, d, m, p, bar);
+    if (threadIdx.x == 0) sdb_mbar_arrive(bar);
+    sdb_mbar_wait(bar, 0);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t n_tiles = (N + 31) / 32, n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tiles; t += n_warps) {
+        const int64_t p0 = t * 32;
+        const int P = (int)((N - p0) < 32 ? (N - p0) : 32);
+        const int64_t pi = p0 + (lane < P ? lane : P - 1);
+        double x[DD], S[MM];
+#pragma unroll UD
+        for (int j = 0; j < DD; ++j)
+            if (j < d) x[j] = pts[pi * d + j];
+#pragma unroll UM
+        for (int k = 0; k < MM; ++k)
+            if (k < m) S[k] = 0.0;
+        sdb_rbf_points_wt<D, M>(sur, d, m, x, S, P);
+        if (lane < P) {
+#pragma unroll UM
+            for (int k = 0; k < MM; ++k)
+                if (k < m) out[pi * m + k] = S[k];
+        }
+    }
+}
+
 extern "C" int sdb_rbf_eval(const double *d_points, int64_t N, int32_t d, int32_t m, const sdb_model *model,
                             double *d_out, void *stream) {
     SDB_CHECK_ARG(model && model->kind == SDB_MODEL_RBF, "sdb_rbf_eval: model must be SDB_MODEL_RBF");
@@ -178,6 +226,23 @@ extern "C" int sdb_rbf_eval(const double *d_points, int64_t N, int32_t d, int32_
     sdb_device_props dp;
     int rc = sdb_get_device_props(&dp);
     if (rc) return rc;
+    {
+        // enough points to give every warp of a persistent grid full 32-point tiles, tables resident: the warp-owned kernel
+        static const bool no_wt = getenv("SDB_NO_WT") != nullptr;
+        const size_t need = 16 + sdb_model_smem_bytes(*model, d, m);
+        if (!no_wt && need <= (size_t)dp.smem_optin && N >= (int64_t)dp.sm_count * 16 * 32 && model->n_centers >= 256) {
+            auto launch_wt = [&](auto kern) -> int {
+                SDB_CUDA(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+                sdb_count_launch();
+                kern<<<dp.sm_count, 512, need, (cudaStream_t)stream>>>(d_points, N, d, m, *model, d_out);
+                SDB_CUDA(cudaGetLastError());
+                return SDB_OK;
+            };
+            if (d == 2 && m == 1) return launch_wt(rbf_eval_wt_kernel<2, 1>);
+            if (d == 4 && m == 3) return launch_wt(rbf_eval_wt_kernel<4, 3>);
+            return launch_wt(rbf_eval_wt_kernel<0, 0>);
+        }
+    }
     const int threads = 256;
     // lanes per point: fill >= 2 CTAs per SM before going wider than one lane per point
     int L = 1;

@@ -161,3 +161,21 @@ def test_f32_surrogate_split_invariance(L):
     sur, truth, _ = _models(2, 1, 1000, 3)
     ref = _run(SIMPLE_PROBLEM, 2, 1, sur, truth, 4000, 8, 0.5, f32=True)
     _same(ref, _run(SIMPLE_PROBLEM, 2, 1, sur, truth, 4000, 8, 0.5, f32=True, coresident=144))
+
+
+@pytest.mark.parametrize("d,m,n", [(2, 1, 1000), (4, 3, 777), (3, 2, 300)])
+def test_stand_alone_evaluation_of_many_points(L, d, m, n):
+    """sdb_rbf_eval with enough points for the persistent warp-owned kernel (rbf_eval_wt_kernel: >= 16 warps x 32 points per
+    SM): 80 007 points (a ragged last tile) against the numpy oracle, all kernel types (surrogate_rbf.py:20-40, 146-173)."""
+    from surrdamh_b200 import surrogate_rbf as SR
+    rs = np.random.RandomState(d * 100 + m)
+    N = 80007
+    centers = rs.standard_normal((n, d))
+    coefs = rs.standard_normal((n + d + 1, m))
+    pts = rs.standard_normal((N, d)) * 1.5
+    for kt in (0, 1, 2, 3, 4, 5, 7):
+        got = SR.Surrogate_apply(d, m, kernel_type=kt).apply([coefs, centers], pts)
+        want = ORB.RbfApply(d, m, kernel_type=kt).apply([coefs, centers], pts)
+        scale = ORB.RbfApply(d, m, kernel_type=kt).apply([np.abs(coefs), centers], np.abs(pts))       # sum |w phi| (+ |tail|)
+        assert got.shape == want.shape == (N, m)
+        assert np.all(np.abs(got - want) <= 1e-10 * np.abs(want) + 64 * 2.2e-16 * np.abs(scale)), kt
