@@ -634,6 +634,22 @@ def solve_alone_ms(run, reps=5):
     return a.elapsed_time(b) / reps
 
 
+def kernel_alone_ms(run, reps=3):
+    """The fused chain kernel of this run's shape on ALL SMs, nothing running beside it (ms per launch)."""
+    torch, blk = run.torch, run.blk
+    run.drain()
+    torch.cuda.synchronize(run.dev)
+    sur = run.state["sur"]
+    blk.run("DAMH", run.K, run.prop, sur, run.truth, trace=run.traces[0])
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        blk.run("DAMH", run.K, run.prop, sur, run.truth, trace=run.traces[0])
+    b.record()
+    b.synchronize()
+    return a.elapsed_time(b) / reps
+
+
 def kernel_name(w):
     if w["surrogate"] == "poly" and w["d"] == 2 and w["m"] == 1 and not os.environ.get("SDB_NO_LEAN"):
         return "chain_lean_kernel<%d,true>" % w["degree"]
@@ -660,6 +676,12 @@ def roofline_of(w, run, rec, peak_tf, peak3_tf, headline):
         out.update({"sms_used": used, "sms_total": sms, "frac_of_the_sms_used": achieved / (peak_tf * used / sms),
                     "sms_note": "the launch leaves %d SMs to the asynchronous collector's kernels; `frac` is against the peak of "
                                 "the WHOLE GPU" % run.reserve_sms})
+        alone = kernel_alone_ms(run)
+        if alone:
+            fl1 = float(C_) * K * per_point
+            out["alone_on_all_sms"] = {"kernel_ms": alone, "achieved": fl1 / (alone * 1e-3) / 1e12, "frac": fl1 / (alone * 1e-3) / 1e12 / peak_tf,
+                                       "note": "the same kernel launched on every SM with nothing beside it (what --collector sync "
+                                               "does), measured after the run: the kernel's own quality"}
     if headline:
         out.update({"traffic_note": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the ncu --set full capture in "
                                     "profiles/r02_chain_kernel_ncu.md; algorithmic bytes = C*K*25 B trace + state = 1.05e8",
