@@ -15,6 +15,9 @@ import os
 import subprocess
 import sys
 
+# the asynchronous collector adds ~8 CUDA streams; with the default 8 hardware launch queues two of them share a queue and serialise
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 
 def main():
     if len(sys.argv) < 3:
