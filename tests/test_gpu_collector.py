@@ -277,3 +277,42 @@ def test_pipelined_collector_equals_the_serial_asynchronous_one(L):
         for a, b in zip(runs[0], runs[1]):
             assert np.array_equal(a, b), lag
         assert np.array_equal(runs[0][3], runs[0][5])            # the updater took over the last round's center set
+
+
+def test_pipelined_collector_failing_round_keeps_previous_model(L):
+    """The pipelined collector on the GPU with a held set that contains a coincident pair ('direct' solve: exact zero pivot) and
+    rounds without snapshots: every round's solve fails, the status log says so, and the model handed to the chains stays the
+    healthy one the collector started from -- coefficients AND centers -- while the thin stage's state keeps the updater's rows."""
+    from surrdamh_b200 import surrogate_rbf as SR
+    from surrdamh_b200.collector import Collector, PipelinedCollector
+    rs = np.random.RandomState(8)
+    n0, K, C_, quota = 300, 2, 64, 32
+    X0 = _prior_points(rs, n0)
+    X0[7] = X0[3]
+    up = SR.Surrogate_update(2, 1, kernel_type=1, solver_type="direct", no_keep=n0)
+    good = SR.Surrogate_update(2, 1, kernel_type=1, solver_type="direct", no_keep=n0)
+    Xg = _prior_points(rs, n0)
+    good.add_arrays(Xg, _toy_G(Xg))
+    model, _ = good.update_device()
+    up._par, up._obs = L.dev(X0), L.dev(_toy_G(X0))
+    col = Collector(up, "rbf", 2, 1, kernel_type=1, snapshots_per_refit=quota)
+    col.model = model
+    before = model.coefs.cpu().numpy().copy()
+    pc = PipelinedCollector(col, "cuda", lag=1)
+    tr, _, _, _ = _random_trace(L, K, C_, 2, 1, seed=1, p_valid=0.0)            # no snapshot at all
+    main = torch.cuda.current_stream()
+    for b in range(3):
+        ev = torch.cuda.Event()
+        ev.record()
+        pc.submit(b, tr, K, ev, b)
+    for b in range(3):
+        ev, mo = pc.result(b)
+        main.wait_event(ev)
+        torch.cuda.synchronize()
+        assert np.array_equal(mo.coefs.cpu().numpy(), before), b            # the pack the pipeline started from, round after round
+        assert np.array_equal(mo.centers.cpu().numpy(), X0), b
+    pc.close()
+    log = col.poll_status(wait=True)
+    assert [s[1] for s in log[-3:]] == [1, 1, 1] and up.round_failures >= 3
+    assert np.array_equal(col.model.coefs.cpu().numpy(), before)
+    assert np.array_equal(up.processed_par, X0)
