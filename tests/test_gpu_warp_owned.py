@@ -179,3 +179,41 @@ def test_stand_alone_evaluation_of_many_points(L, d, m, n):
         scale = ORB.RbfApply(d, m, kernel_type=kt).apply([np.abs(coefs), centers], np.abs(pts))       # sum |w phi| (+ |tail|)
         assert got.shape == want.shape == (N, m)
         assert np.all(np.abs(got - want) <= 1e-10 * np.abs(want) + 64 * 2.2e-16 * np.abs(scale)), kt
+
+
+def test_split_phases_use_the_warp_owned_shape_and_change_nothing(L):
+    """PROPOSE / DECIDE launches (host-evaluated G, classes_SAMPLER.py:77-81 through the solver plugin) with a 1200-center RBF surrogate
+    -- the library picks the warp-owned shape on its own -- against the fused launch with the zero model as G: identical samples,
+    counters and posteriors, also when the two phases are issued for two halves of the chains (the pipelined split path)."""
+    from surrdamh_b200.chains import ChainBlock, Proposal, Trace
+    from surrdamh_b200.device import DeviceModel, DeviceProblem
+    d, m, C_, K = 2, 1, 2500, 7
+    rs = np.random.RandomState(12)
+    centers = rs.standard_normal((1200, 2)) * 2.0 + np.array([5.0, 3.0])
+    coefs = rs.standard_normal((1203, 1)) * 1e-9
+    coefs[1200:, 0] = [2e-5, -1e-5, -1.05e-3]
+    sur, zero = DeviceModel.rbf(coefs, centers, 1), DeviceModel.zero(d, m)
+    prop = Proposal(d, [0.4, 0.2])
+    prob = DeviceProblem(d, **SIMPLE_PROBLEM)
+
+    fused = ChainBlock(prob, C_, seed=21)
+    assert fused.plan("DAMH", sur, zero, prop)["lanes_per_chain"] == 0          # warp-owned, chosen by the library
+    fused.prepare("DAMH", sur, zero)
+    fused.run("DAMH", K, prop, sur, zero)
+    torch.cuda.synchronize()
+    assert int(fused.counters[0].sum()) > 0 and int(fused.counters[2].sum()) > 0
+
+    for halves in ([(0, C_)], [(0, 1100), (1100, C_ - 1100)]):
+        blk = ChainBlock(prob, C_, seed=21)
+        G0 = np.zeros((C_, m))
+        blk.prepare("DAMH", sur, None, G_host=G0)
+        one = Trace(1, C_, d, m, blk.device, snapshots=False)
+        Gd = torch.zeros((m, C_), dtype=torch.float64, device=blk.device)
+        for k in range(K):
+            for lo, n in halves:
+                blk.propose("DAMH", prop, sur, one, chains=(lo, n), step0=k)
+            for i, (lo, n) in enumerate(halves):
+                blk.decide("DAMH", prop, sur, one, Gd, chains=(lo, n), advance=(i == len(halves) - 1), step0=k)
+        torch.cuda.synchronize()
+        for a, b in ((fused.u, blk.u), (fused.counters, blk.counters), (fused.post_u, blk.post_u), (fused.pre_u, blk.pre_u)):
+            assert torch.equal(a, b), halves
