@@ -376,6 +376,8 @@ class Run:
         self.col = self.acol = None
         self.lag = lag if collector != "sync" else 0
         self.reserve_sms = reserve_sms if collector != "sync" else 0
+        if w["updated"] and self.updater.uses_cluster_kernels():
+            self.reserve_sms = 0          # the LU's 16-CTA cluster cannot be placed on scattered SMs: the round runs between blocks
         if w["updated"]:
             self.col = Collector(self.updater, "rbf", d, m, kernel_type=w["kernel_type"], rank=rank, world=world,
                                  snapshots_per_refit=w["snapshots_per_refit"], refit_mode=refit_mode, device=dev)

@@ -168,8 +168,10 @@ class LockstepSampler:
                     surrogate, swapped = new, True
             strm = None if self.streams is None else self.streams(i, done, K)
             if self.truth is not None:
-                blk.run(kind, K, prop, surrogate, self.truth, trace=trace, streams=strm, refresh_pre=swapped,
-                        coresident=self.conf.reserve_sms if acol is not None else 0)
+                reserve = 0
+                if acol is not None and not getattr(col.updater, "uses_cluster_kernels", lambda: False)():
+                    reserve = self.conf.reserve_sms
+                blk.run(kind, K, prop, surrogate, self.truth, trace=trace, streams=strm, refresh_pre=swapped, coresident=reserve)
             else:
                 self._run_split(kind, K, prop, surrogate, trace, strm, swapped, collects)
             swapped = False

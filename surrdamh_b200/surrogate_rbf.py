@@ -121,6 +121,13 @@ class Surrogate_update:
             self._work = torch.empty((need,), dtype=torch.float64, device="cuda")
         return self._work
 
+    def uses_cluster_kernels(self):
+        """True when the dense solve is the LU with partial pivoting (solver_type 'direct', or a kernel type the null-space
+        Cholesky does not cover): its panel kernel is a 16-CTA thread-block cluster, which cannot be placed on the scattered SMs a
+        chain kernel leaves to an asynchronous collector -- such a collector must not ask the chains to reserve SMs (its round then
+        runs when a chain block ends, like the synchronous one, but still off the host's critical path)."""
+        return not (self.solver_type == "nullspace" and int(self.kernel_type) in (0, 1, 4, 5, 6))
+
     def _solve_dense(self, Xb, Yb, Cb, n, info):
         """Dense solve of the saddle system for the n rows of (Xb, Yb) into Cb; launches only (info stays on the device)."""
         d, m = self.no_parameters, self.no_observations
