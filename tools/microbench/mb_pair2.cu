@@ -34,6 +34,29 @@ __global__ void __launch_bounds__(512, 1) pass8(double *out, int iters, int n) {
                 const double t = r2 * y;
                 const double e = fma(-t, y, 1.0);
                 if (V == 5) { const double a = r2 * t; acc[p] = fma(fma(a, 0.5 * e, a), wk, acc[p]); continue; }   // second-order: 2 FP64 fewer
+                if (V == 6) {   // the e^2 term of the correction in FP32 (two conversions + two FP32 operations), 10 FP64
+                    const float ef = (float)e;
+                    const double q2 = (double)(0.375f * ef * ef);
+                    const double qq = fma(0.5, e, q2);
+                    const double a = r2 * t;
+                    acc[p] = fma(fma(a, qq, a), wk, acc[p]);
+                    continue;
+                }
+                if (V == 7) {   // the same with the e^2 term from the HIGH WORD of e through integer / FP32 operations only (no F2F)
+                    const int hi = __double2hiint(e);                       // sign, 11-bit exponent, 20 mantissa bits
+                    // float with the same value as the truncated e: exponent re-biased (1023 -> 127), mantissa shifted by 3
+                    const int fb = ((hi & 0x7fffffff) >> 3 << 0) - ((1023 - 127) << 20 >> 0 << 0) * 0;   // placeholder, replaced below
+                    (void)fb;
+                    const unsigned mag = (unsigned)(hi & 0x7fffffff);
+                    const float ef = __uint_as_float(mag > (896u << 20) ? ((mag - (896u << 20)) << 3) : 0u);   // |e| as a float (sign irrelevant for e^2)
+                    const float q2f = 0.375f * ef * ef;
+                    const unsigned qb = __float_as_uint(q2f);
+                    const double q2 = __hiloint2double((int)(qb ? ((qb >> 3) + (896u << 20)) : 0u), (int)(qb << 29));
+                    const double qq = fma(0.5, e, q2);
+                    const double a = r2 * t;
+                    acc[p] = fma(fma(a, qq, a), wk, acc[p]);
+                    continue;
+                }
                 const double q = e * fma(0.375, e, 0.5);
                 const double a = r2 * t;
                 acc[p] = fma(fma(a, q, a), wk, acc[p]);
@@ -75,6 +98,8 @@ int main() {
     run<2>("V2 weight a constant (the accumulating FMA reads 2 registers)", 11, out);
     run<3>("V3 both", 12, out);
     run<4>("V4 distance + accumulate only (5 FP64)", 5, out);
-    run<5>("V5 second-order correction (9 FP64 + MUFU)", 9, out);
+    run<5>("V5 second-order correction (10 FP64 + MUFU)", 10, out);
+    run<6>("V6 e^2 term in FP32 via two F2F conversions (10 FP64 + MUFU)", 10, out);
+    run<7>("V7 e^2 term in FP32 via integer re-biasing, no F2F (10 FP64)", 10, out);
     return 0;
 }
