@@ -349,13 +349,19 @@ class Surrogate_update:
         status[0] = bad.to(torch.float64)
         status[1] = sb["info"][0].to(torch.float64)
         status[2:4] = meta[0:2]
+        status[4] = X.sum() + Y.sum()          # checksum of the rows these coefficients belong to (see assemble)
 
     def assemble(self, result, X, Y, pack_prev, pack_out):
-        """pack_out = [COEFS of result | X | Y | status], or a copy of pack_prev when the round's solve failed."""
+        """pack_out = [COEFS of result | X | Y | status], or a copy of pack_prev when the round's solve failed -- or when
+        the coefficients were fitted to OTHER rows than this rank's thinned set (every rank thins for itself; the checksum
+        the solving rank sends along catches a rank whose thinning diverged, status[5] = 1)."""
         n0, d, m = int(self.no_keep), self.no_parameters, self.no_observations
         o_c, o_x, o_y, o_s, _ = self.pack_layout(n0, d, m)
         r_s, _ = self.result_layout()
         status = result[r_s:r_s + 16]
+        mismatch = status[4] != (X.sum() + Y.sum())
+        status[5] = mismatch.to(torch.float64)
+        status[0] = torch.maximum(status[0], status[5])
         pack_out[o_c:o_c + (n0 + d + 1) * m].copy_(result[:(n0 + d + 1) * m])
         pack_out[o_x:o_x + n0 * d].copy_(X.reshape(-1))
         pack_out[o_y:o_y + n0 * m].copy_(Y.reshape(-1))
