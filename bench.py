@@ -74,7 +74,7 @@ def static_config(wname, w):
             "poly_degree": w.get("degree"), "surrogate_is_updated": bool(w["updated"]),
             "refit_every": w["block"] if w["updated"] else None,
             "snapshots_per_refit": w.get("snapshots_per_refit") if w["updated"] else None,
-            "collector": "asynchronous, deterministic lag of one block (the reference's collector is a separate process)" if w["updated"] else None,
+            "collector": "asynchronous with a deterministic lag (collector.lag_blocks; the reference's collector is a separate process)" if w["updated"] else None,
             "proposal_std": w["proposal_std"], "true_model": w["truth"],
             "l2": "GPU arm: 256 MiB flush write before every bench step, inside the timed region"}
 
@@ -740,6 +740,15 @@ def run_ours(args):
         w["solver_type"] = args.solver
     collector = args.collector or "async"
     refit_mode = args.refit_mode or ("rotate" if world > 1 else "broadcast")
+    # How many SMs the collector needs beside the chains, and the lag that goes with it.  One GPU solves every round itself: the
+    # dense solve (2.3e10 flop) must fit one block period, which takes ~15 SMs (lag 1).  With the solve duty rotating over N GPUs a
+    # rank solves every N-th round and may take N periods for it, so it gets by with fewer SMs (and the chains get more), at the
+    # price of a surrogate that is a block or two older: 11 SMs / lag 2 on 2 GPUs, 6 SMs / lag 3 from 4 GPUs on (measured, 4 GPUs:
+    # 14.55 -> 13.66 ms per step).  The strong-scaling record keeps 15 SMs: its blocks shrink with N, its solve window does not grow.
+    auto_r, auto_lag = {1: (15, 1), 2: (11, 2)}.get(world, (6, 3)) if refit_mode == "rotate" or world == 1 else (15, 1)
+    weak_reserve = args.reserve_sms or auto_r
+    weak_lag = args.lag or auto_lag
+    strong_reserve = args.reserve_sms or 15
 
     # ---- CPU baseline (rank 0, N == 1 only), before the timed GPU region -------------------------------
     cpu = None
@@ -750,7 +759,7 @@ def run_ours(args):
             cpu["refit_s"] = fit_s
             cpu["refit_note"] = "one full Surrogate_update.update() of the same CPU implementation at n = %d (solver_type 'direct', all host threads)" % WORKLOADS[wname]["centers"]
 
-    run = Run(w, w["chains"], rank, world, dev, collector, refit_mode, args.lag, reserve_sms=args.reserve_sms)
+    run = Run(w, w["chains"], rank, world, dev, collector, refit_mode, weak_lag, reserve_sms=weak_reserve)
     if args.profile:
         run.warmup(max(args.warmup, 3))
         torch.cuda.synchronize(dev)
@@ -775,19 +784,19 @@ def run_ours(args):
     strong = None
     if world > 1 and w["updated"] and not args.no_extras and w["chains"] % world == 0:
         slag = args.strong_lag or world
-        srun = Run(w, w["chains"] // world, rank, world, dev, collector, refit_mode, slag, reserve_sms=args.reserve_sms)
+        srun = Run(w, w["chains"] // world, rank, world, dev, collector, refit_mode, slag, reserve_sms=strong_reserve)
         srec = srun.measure(args.steps, args.warmup, e2e_steps)
         strong = {"scaling": "strong", "chains_total": w["chains"], "chains_per_gpu": w["chains"] // world, "value": srec["value"],
                   "unit": "chain steps/s", "ms_per_step": srec["ms_per_step"], "e2e": srec["e2e"],
                   "kernel_ms": float(np.mean([k for k, _ in srec["kern"]])),
                   "round_ms": float(np.mean(srec["rounds"])) if srec["rounds"] else None, "gpu_launches": srec["launches"],
-                  "lag_blocks": srun.lag, "stages_ms": srec.get("stages")}
+                  "lag_blocks": srun.lag, "reserved_sms": srun.reserve_sms, "stages_ms": srec.get("stages")}
         del srun
 
     # ---- the FP32-surrogate variant of the same workload (second line; the headline stays FP64) ---------------------------
     fp32 = None
     if w["surrogate"] == "rbf" and not args.no_extras:
-        frun = Run(w, w["chains"], rank, world, dev, collector, refit_mode, args.lag, precision="f32", reserve_sms=args.reserve_sms)
+        frun = Run(w, w["chains"], rank, world, dev, collector, refit_mode, weak_lag, precision="f32", reserve_sms=strong_reserve)
         frec = frun.measure(max(10, args.steps // 2), 3, 2)
         if rank == 0:
             p32 = fp32_peak(dev)
@@ -933,9 +942,10 @@ def main():
                     help="async (default): the collector round runs on a side stream beside the next block and its surrogate is "
                          "used from block b+2 on, like the reference's separate collector process; sync: between blocks")
     ap.add_argument("--refit-mode", default="", choices=["", "broadcast", "rotate", "replicated"])
-    ap.add_argument("--lag", type=int, default=1, help="blocks of lag of the asynchronous collector (weak-scaling record)")
+    ap.add_argument("--lag", type=int, default=0, help="blocks of lag of the asynchronous collector, weak-scaling record (0: by the number of GPUs)")
     ap.add_argument("--strong-lag", type=int, default=0, help="the same for the strong-scaling record (0: the number of GPUs)")
-    ap.add_argument("--reserve-sms", type=int, default=15, help="SMs the chain kernel leaves to the asynchronous collector's kernels")
+    ap.add_argument("--reserve-sms", type=int, default=0,
+                    help="SMs the chain kernel leaves to the asynchronous collector's kernels, weak-scaling record (0: by the number of GPUs)")
     ap.add_argument("--profile", type=int, default=0, help="run this many bench steps inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -827,8 +827,11 @@ static int ns_enqueue(cudaStream_t st, double *S, int64_t ld, int n, int d, int 
         // a cooperative grid starts only when ALL its CTAs fit at once: 64 CTAs could not start on the SMs an asynchronous
         // collector has beside the chain kernel and the round waited for the chain block to end.  16 CTAs carry the same
         // critical path (measured, whole round on 148 SMs: 3.75 ms with 64 or 32 CTAs, 3.77 with 16, 3.85 with 8).
-        static const int bwd_cap = getenv("SDB_BWD_GRID") ? atoi(getenv("SDB_BWD_GRID")) : 16;
-        if (bwd_cap > 0 && grid > bwd_cap) grid = bwd_cap;
+        // With a rotating solve duty on several GPUs the collector gets as few as 6 SMs (two CTAs of this kernel each): 8 CTAs up
+        // to 64 blocks (n <= 4096), 16 beyond.
+        static const int bwd_env = getenv("SDB_BWD_GRID") ? atoi(getenv("SDB_BWD_GRID")) : 0;
+        const int bwd_cap = bwd_env > 0 ? bwd_env : (nblk <= 64 ? 8 : 16);
+        if (grid > bwd_cap) grid = bwd_cap;
         if (grid < 1) { sdb_set_error("sdb_rbf_fit_nullspace: the backward-solve kernel does not fit on the device"); return SDB_ERR_CUDA; }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
