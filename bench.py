@@ -506,7 +506,7 @@ class Run:
                   "rounds": [[base.elapsed_time(e) if e is not None else None for e in (t0_, g, t, s_, m_)]
                              for t0_, t, s_, m_, g in self.acol.stage_events],
                   "columns": "blocks: chain kernel start, end; rounds: start, gathered, thinned, solved (duty rank), assembled"}
-            with open("%s_c%d_rank%d.json" % (os.environ["SDB_TIMELINE"], self.C, self.rank), "w") as f:
+            with open("%s_c%d_%s_rank%d.json" % (os.environ["SDB_TIMELINE"], self.C, self.precision, self.rank), "w") as f:
                 json.dump(tl, f)
         stages = None
         if getattr(self.acol, "stage_events", None):

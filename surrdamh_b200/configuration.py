@@ -22,7 +22,10 @@ ADDITIVE keys of this implementation (ignored by the reference, never renames):
   collector_pipelined  (with collector_async, default true) the round runs as two pipelined stages -- thinning on every
                        rank, the dense solve on the rank on duty -- so consecutive rounds overlap (PipelinedCollector)
   reserve_sms          SMs the chain kernel leaves free for the asynchronous collector's kernels (default 15; the
-                       chain CTAs own their SMs, so the refit needs SMs of its own to run beside them)
+                       chain CTAs own their SMs, so the refit needs SMs of its own to run beside them).  One GPU must
+                       solve every round within a block period: ~15 SMs at 4096 centers.  With refit_mode "rotate" on N
+                       GPUs a rank solves every N-th round: 11 SMs with refit_lag 2 on two GPUs, 6 SMs with refit_lag 3
+                       from four on leave the chains more SMs (what bench.py uses)
   surrogate_precision  'f64' (default, the reference's arithmetic) | 'f32': an RBF surrogate is evaluated on the FP32
                        pipe inside the chain kernel (stage 1 only screens; stage 2 keeps the chain exact)
   drop_coincident      remove exactly coincident snapshots before an RBF solve (default true: lockstep chains
