@@ -746,6 +746,10 @@ def run_ours(args):
     # price of a surrogate that is a block or two older: 11 SMs / lag 2 on 2 GPUs, 6 SMs / lag 3 from 4 GPUs on (measured, 4 GPUs:
     # 14.55 -> 13.66 ms per step).  The strong-scaling record keeps 15 SMs: its blocks shrink with N, its solve window does not grow.
     auto_r, auto_lag = {1: (15, 1), 2: (11, 2)}.get(world, (6, 3)) if refit_mode == "rotate" or world == 1 else (15, 1)
+    # the cooperative backward solve of the refit must fit on the reserved SMs (two CTAs each): 16 CTAs where >= 11 SMs are
+    # reserved, the library's default of 8 (n <= 4096) with 6.  Read once by the library, before its first fit.
+    if world <= 2:
+        os.environ.setdefault("SDB_BWD_GRID", "16")
     weak_reserve = args.reserve_sms or auto_r
     weak_lag = args.lag or auto_lag
     strong_reserve = args.reserve_sms or 15
