@@ -396,10 +396,11 @@ class PipelinedCollector(AsyncCollector):
             ev = self.thin.record()
             with self.solve:
                 self.solve.wait(ev)
-                scratch = self.slots[0]
-                scratch["meta"][0] = float(int(up.no_keep))
+                _, _, meta0 = up.new_thin_state()        # buffers of their own: slot 0 belongs to the first round already
+                self._prime = (meta0, up.new_result())
+                meta0[0] = float(int(up.no_keep))
                 for _ in range(2):
-                    up.solve_stage(s0["X"], s0["Y"], scratch["meta"], scratch["result"])
+                    up.solve_stage(s0["X"], s0["Y"], meta0, self._prime[1])
 
     def submit(self, b, trace, K, chain_done_event, step, timed=False):
         col, up = self.col, self.col.updater
